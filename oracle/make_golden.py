@@ -1,0 +1,269 @@
+"""TEST INFRASTRUCTURE ONLY.  Generates tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference: models/blocks.py, models/architectures.py, utils/loss.py,
+datasets/dataloader.py + the reference C++ through oracle/_ref) on seeded inputs, and pins
+the oracle restatements (oracle/model_ref.py, oracle/d3feat_oracle.c) against it.
+
+Run in the build container only (the reference tree is absent on the GPU box):
+    python oracle/make_golden.py
+Inputs are NOT stored: they are regenerated from seeds by tests/_inputs.py and
+d3feat/pytorch_b200/synthetic.py; fixtures hold the reference's OUTPUTS.
+"""
+import contextlib
+import io
+import os
+import sys
+import types
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+REF = "/root/reference"
+GOLD = os.path.join(REPO, "tests", "golden")
+sys.dont_write_bytecode = True
+
+import torch  # noqa: E402
+
+from oracle import cpu, model_ref  # noqa: E402
+import _inputs  # noqa: E402
+from d3feat.pytorch_b200 import synthetic  # noqa: E402
+from d3feat.pytorch_b200.config import default_config, build_architecture  # noqa: E402
+
+
+def import_reference():
+    """stub open3d + the two CPython extensions, cwd = reference root."""
+    sys.path.insert(0, REF)
+    os.chdir(REF)  # kernels/kernel_points.py:403 uses the relative path 'kernels/dispositions'
+    sys.modules["open3d"] = types.ModuleType("open3d")
+    pkg = types.ModuleType("cpp_wrappers"); pkg.__path__ = []
+    sub = types.ModuleType("cpp_wrappers.cpp_subsampling"); sub.__path__ = []
+    nei = types.ModuleType("cpp_wrappers.cpp_neighbors"); nei.__path__ = []
+    gs = types.ModuleType("cpp_wrappers.cpp_subsampling.grid_subsampling")
+    rn = types.ModuleType("cpp_wrappers.cpp_neighbors.radius_neighbors")
+
+    def subsample_batch(points, batches, sampleDl=0.1, max_p=0, verbose=0, **kw):
+        assert not kw
+        return cpu.subsample_batch(points, batches, sampleDl, max_p, impl="ref")
+
+    def batch_query(queries, supports, q_batches, s_batches, radius=0.1):
+        return cpu.batch_query(queries, supports, q_batches, s_batches, radius, impl="ref")
+
+    gs.subsample_batch = subsample_batch
+    rn.batch_query = batch_query
+    sub.grid_subsampling = gs
+    nei.radius_neighbors = rn
+    for m in (pkg, sub, nei, gs, rn):
+        sys.modules[m.__name__] = m
+    import models.blocks as rblocks
+    import models.architectures as rarch
+    import utils.loss as rloss
+    import datasets.dataloader as rdata
+    return rblocks, rarch, rloss, rdata
+
+
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def save(name, **arrs):
+    path = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(path, **{k: np.asarray(v) for k, v in arrs.items()})
+    print("wrote %-28s %7.1f KB" % (name + ".npz", os.path.getsize(path) / 1024))
+
+
+def ref_kpconv_module(rblocks, case, cin, cout, deformable, modulated, influence, aggregation):
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = rblocks.KPConv(15, 3, cin, cout, case["extent"], case["radius"], KP_influence=influence,
+                           aggregation_mode=aggregation, deformable=deformable, modulated=modulated)
+    sd = {k: v.clone() for k, v in case["sd"].items()}
+    missing = m.load_state_dict(sd, strict=True)
+    return m
+
+
+def golden_kpconv(rblocks):
+    cases = [
+        # name, n, cin, cout, deformable, modulated, influence, aggregation, neighbour radius factor
+        ("kpconv_rigid_2k", 2000, 64, 64, False, False, "linear", "sum", 1.0),       # BASELINE config 1
+        ("kpconv_rigid_c1", 1500, 1, 64, False, False, "linear", "sum", 1.0),        # first layer Cin=1, ones
+        ("kpconv_gauss_closest", 600, 16, 24, False, False, "gaussian", "closest", 1.0),
+        ("kpconv_constant", 600, 16, 8, False, False, "constant", "sum", 1.0),
+        ("kpconv_deform", 800, 32, 32, True, False, "linear", "sum", 2.0),
+        ("kpconv_deform_mod", 800, 16, 32, True, True, "linear", "sum", 2.0),
+        ("kpconv_deform_gauss", 500, 16, 16, True, False, "gaussian", "sum", 2.0),
+    ]
+    for ci, (name, n, cin, cout, deform, mod, infl, agg, rf) in enumerate(cases):
+        case = _inputs.kpconv_case(n=n, cin=cin, cout=cout, seed=100 + ci, deformable=deform, modulated=mod)
+        if cin == 1:
+            case["x"] = np.ones_like(case["x"])
+        lens = np.array([n], np.int32)
+        inds = cpu.batch_query(case["pts"], case["pts"], lens, lens, case["radius"] * rf, impl="ref")
+        m = ref_kpconv_module(rblocks, case, cin, cout, deform, mod, infl, agg)
+        pts = t(case["pts"])
+        x = t(case["x"]).requires_grad_(True)
+        out = m(pts, pts, t(inds).long(), x)
+        (out * t(case["g"])).sum().backward()
+        grads = {"d_" + k.replace(".", "__"): p.grad.numpy() for k, p in m.named_parameters() if p.grad is not None}
+        extra = {}
+        if deform:
+            extra = dict(min_d2=m.min_d2.detach().numpy(), deformed_KP=m.deformed_KP.detach().numpy())
+        # pin the restatement (fwd + bwd) against the reference
+        sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "kernel_points" not in k)
+              for k, v in case["sd"].items()}
+        x2 = t(case["x"]).requires_grad_(True)
+        out2 = model_ref.kpconv(pts, pts, t(inds), x2, sd, "", case["extent"], influence=infl, aggregation=agg,
+                                deformable=deform, modulated=mod)
+        (out2 * t(case["g"])).sum().backward()
+        e = [rel(out2.detach(), out.detach()), rel(x2.grad, x.grad), rel(sd["weights"].grad, m.weights.grad)]
+        if deform:
+            e.append(rel(sd["offset_conv.weights"].grad, m.offset_conv.weights.grad))
+            e.append(rel(sd["offset_bias"].grad, m.offset_bias.grad))
+        print("  %-22s restatement vs reference (rel max): %s" % (name, ["%.1e" % v for v in e]))
+        assert max(e) < 2e-5, (name, e)
+        save(name, inds=inds.astype(np.int32), out=out.detach().numpy(), dx=x.grad.numpy(), **grads, **extra)
+
+
+def golden_native():
+    p0 = synthetic.room_shell_fragment(1800, 11)
+    p1 = synthetic.room_shell_fragment(1400, 12)
+    pts = np.concatenate([p0, p1])
+    lens = np.array([1800, 1400], np.int32)
+    out = {}
+    r = 0.075
+    for lvl in range(3):
+        nb = cpu.batch_query(pts, pts, lens, lens, r, impl="ref")
+        sp, sl = cpu.subsample_batch(pts, lens, 2 * r / 2.5, impl="ref")
+        pool = cpu.batch_query(sp, pts, sl, lens, r, impl="ref")
+        up = cpu.batch_query(pts, sp, lens, sl, 2 * r, impl="ref")
+        # pin the C restatement
+        nb2 = cpu.batch_query(pts, pts, lens, lens, r, impl="port")
+        sp2, sl2 = cpu.subsample_batch(pts, lens, 2 * r / 2.5, impl="port")
+        assert np.array_equal(sp.view(np.uint32), sp2.view(np.uint32)) and np.array_equal(sl, sl2)
+        assert nb.shape == nb2.shape
+        print("  level %d: N=%d H=%d  port-vs-ref index mismatches (tie order only): %d" %
+              (lvl, pts.shape[0], nb.shape[1], int((nb != nb2).sum())))
+        out.update({"nb%d" % lvl: nb, "sub%d" % lvl: sp, "sublen%d" % lvl: sl, "pool%d" % lvl: pool, "up%d" % lvl: up})
+        pts, lens, r = sp, sl, r * 2
+    save("native_pyramid", **out)
+
+
+def small_config(**kw):
+    return default_config(first_features_dim=32, **kw)
+
+
+def golden_model(rblocks, rarch, rloss, rdata):
+    for name, kw, n in [("kpfcnn_rigid", {}, 1500),
+                        ("kpfcnn_deform", dict(architecture=build_architecture(5, deformable_from=3)), 1500)]:
+        cfg = small_config(**kw)
+        data = synthetic.fragment_pair(n, seed=5, num_node=64)
+        limits = [40, 40, 40, 40, 40] if "deform" not in name else [40, 40, 40, 120, 120]
+        batch = rdata.collate_fn_descriptor([data], cfg, limits)
+        torch.manual_seed(0); np.random.seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = rarch.KPFCNN(cfg)
+        shapes, kpr = _inputs.kpfcnn_shapes(cfg)
+        ref_sd = model.state_dict()
+        assert set(ref_sd) == set(shapes) | set(kpr), set(ref_sd) ^ (set(shapes) | set(kpr))
+        for k in shapes:
+            assert tuple(ref_sd[k].shape) == tuple(shapes[k]), k
+        for k, rad in kpr.items():
+            mod = model
+            for part in k.split(".")[:-1]:
+                mod = getattr(mod, part) if not part.isdigit() else mod[int(part)]
+            assert abs(mod.radius - rad) < 1e-9, k
+        sd = _inputs.kpfcnn_state_dict(cfg, seed=3)
+        model.load_state_dict(sd, strict=True)
+        model.train()
+        feats, scores = model(batch)
+        c = batch["corr"].long()
+        n0 = int(batch["stack_lengths"][0][0])
+        circle = rloss.CircleLoss(dist_type="euclidean", log_scale=10, safe_radius=0.1, pos_margin=0.1, neg_margin=1.4)
+        dl, acc, fp, an, _, dists = circle(feats[c[:, 0]], feats[c[:, 1] + n0], batch["dist_keypts"])
+        det = rloss.DetLoss()(dists, scores[c[:, 0]], scores[c[:, 1] + n0])
+        (dl + det).backward()
+        gnorm = {k: float(p.grad.norm()) for k, p in model.named_parameters() if p.grad is not None}
+        # restatement
+        sd2 = {k: v.clone().requires_grad_("kernel_points" not in k) for k, v in sd.items()}
+        f2, s2 = model_ref.kpfcnn_forward(sd2, batch, cfg, training=True)
+        dl2, det2, acc2, d2 = model_ref.pair_losses(f2, s2, batch, "circle")
+        (dl2 + det2).backward()
+        e = [rel(f2.detach(), feats.detach()), rel(s2.detach(), scores.detach()), rel(dl2.detach(), dl.detach()),
+             rel(det2.detach(), det.detach()),
+             max(abs(float(sd2[k].grad.norm()) - g) / max(g, 1e-12) for k, g in gnorm.items())]
+        print("  %-14s restatement vs reference: %s" % (name, ["%.1e" % v for v in e]))
+        assert max(e) < 5e-5, e
+        model.eval()
+        with torch.no_grad():
+            _, scores_eval = model(batch)
+            _, s_eval2 = model_ref.kpfcnn_forward(sd, batch, cfg, training=False)
+        assert rel(s_eval2, scores_eval) < 1e-5
+        keys = sorted(gnorm)
+        save(name, features=feats.detach().numpy(), scores=scores.detach().numpy(),
+             scores_eval=scores_eval.numpy(), desc_loss=dl.detach().numpy(), det_loss=det.detach().numpy(),
+             acc=np.float32(acc), grad_keys=np.array(keys), grad_norms=np.array([gnorm[k] for k in keys]),
+             N=np.array([p.shape[0] for p in batch["points"]]),
+             H=np.array([p.shape[1] for p in batch["neighbors"]]),
+             nb_sum=np.array([int(x.sum()) for x in batch["neighbors"]], np.int64),
+             pool_sum=np.array([int(x.sum()) for x in batch["pools"]], np.int64),
+             up_sum=np.array([int(x.sum()) for x in batch["upsamples"]], np.int64))
+
+
+def golden_loss(rloss):
+    rng = np.random.default_rng(42)
+    out = {}
+    for P in (128, 64, 7):
+        a = rng.standard_normal((P, 32)); a /= np.linalg.norm(a, axis=1, keepdims=True)
+        p = a + 0.25 * rng.standard_normal((P, 32)); p /= np.linalg.norm(p, axis=1, keepdims=True)
+        kp = rng.random((P, 3)) * 0.6
+        dk = np.sqrt(((kp[:, None] - kp[None]) ** 2).sum(-1))
+        sa, sp = rng.random((P, 1)).astype(np.float32), rng.random((P, 1)).astype(np.float32)
+        for kind in ("circle", "contrastive"):
+            A = t(a.astype(np.float32)).requires_grad_(True)
+            B = t(p.astype(np.float32)).requires_grad_(True)
+            SA, SP = t(sa).requires_grad_(True), t(sp).requires_grad_(True)
+            mod = (rloss.CircleLoss(dist_type="euclidean", log_scale=10, safe_radius=0.1, pos_margin=0.1, neg_margin=1.4)
+                   if kind == "circle" else rloss.ContrastiveLoss(pos_margin=0.1, neg_margin=1.4, metric="euclidean", safe_radius=0.1))
+            loss, acc, fp, an, _, dists = mod(A, B, t(dk))
+            det = rloss.DetLoss()(dists, SA, SP)
+            (loss + det).backward()
+            A2 = t(a.astype(np.float32)).requires_grad_(True)
+            B2 = t(p.astype(np.float32)).requires_grad_(True)
+            SA2, SP2 = t(sa).requires_grad_(True), t(sp).requires_grad_(True)
+            fn = model_ref.circle_loss if kind == "circle" else model_ref.contrastive_loss
+            l2, acc2, fp2, an2, d2 = fn(A2, B2, t(dk), safe_radius=0.1)
+            det2 = model_ref.det_loss(d2, SA2, SP2)
+            (l2 + det2).backward()
+            e = [rel(l2.detach(), loss.detach()), rel(det2.detach(), det.detach()), rel(A2.grad, A.grad),
+                 rel(B2.grad, B.grad), rel(SA2.grad, SA.grad), rel(d2.detach(), dists.detach()),
+                 rel(fp2.detach(), np.array(fp)), rel(an2.detach(), np.array(an)), abs(float(acc2) - float(acc))]
+            print("  loss %-11s P=%-3d restatement vs reference: max %.1e" % (kind, P, max(e)))
+            assert max(e) < 1e-5, e
+            pre = "%s%d_" % (kind, P)
+            out.update({pre + "loss": loss.detach().numpy(), pre + "det": det.detach().numpy(), pre + "acc": np.float32(acc),
+                        pre + "dA": A.grad.numpy(), pre + "dB": B.grad.numpy(), pre + "dSA": SA.grad.numpy(),
+                        pre + "dSP": SP.grad.numpy(), pre + "fp": np.array(fp, np.float32), pre + "an": np.array(an, np.float32)})
+        for metric in ("cosine", "sqeuclidean", "cityblock", "arccosine"):
+            d = rloss.cdist(t(a.astype(np.float32)), t(p.astype(np.float32)), metric)
+            assert rel(model_ref.cdist(t(a.astype(np.float32)), t(p.astype(np.float32)), metric), d) < 1e-6
+            if P == 64:
+                out["cdist_" + metric] = d.numpy()
+    save("losses", **out)
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    cpu.build()
+    rblocks, rarch, rloss, rdata = import_reference()
+    print("native (radius neighbours / grid subsampling):"); golden_native()
+    print("KPConv layers:"); golden_kpconv(rblocks)
+    print("losses:"); golden_loss(rloss)
+    print("KPFCNN harness:"); golden_model(rblocks, rarch, rloss, rdata)
+
+
+if __name__ == "__main__":
+    main()
