@@ -1,0 +1,14 @@
+#include "common.cuh"
+#include <stdarg.h>
+
+static thread_local char g_err[512] = "no error";
+
+void d3f_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" int d3f_version(void) { return 100; }
+extern "C" const char* d3f_last_error_string(void) { return g_err; }

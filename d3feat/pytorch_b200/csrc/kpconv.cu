@@ -1,0 +1,584 @@
+// KPConv forward / backward (replaces the ATen chain of models/blocks.py:237-382).
+//
+// Math per query i:
+//   w[i,k,h]  = influence(|| (s[idx[i,h]] - q[i]) - kp[k] ||^2)           (shadow idx -> no contribution)
+//   wf[i,k,:] = m[i,k] * sum_h w[i,k,h] * x[idx[i,h], :]
+//   out[i,:]  = (sum_k wf[i,k,:] @ W[k]) / max(1, #{h : sum_c x[idx[i,h],c] > 0})
+//
+// Kernels
+//   kp_rowpos     : per support row, (sum_c x[j,c] > 0)                      (density count, blocks.py:377)
+//   kp_correlate  : one warp per query.  Phase 1: lanes over neighbours compute the K influences into
+//                   shared memory (+ in-range filter / min_d2 for deformed kernels).  Phase 2: lanes over
+//                   channels gather each neighbour row once (coalesced) and accumulate all K products
+//                   in registers; wf is written [Nq, K*Cin] row-major = the A operand of the contraction.
+//   kp_gemm       : fp32 tiled GEMM (NN / NT / TN, optional split-K) used for
+//                   out = diag(inv_n) wf W,  dwf = diag(inv_n) g W^T,  dW = wf^T diag(inv_n) g
+//   kp_scatter    : one warp per query: dx[idx] += sum_k w dwf  (+ kernel-point / modulation grads)
+#include "common.cuh"
+
+namespace {
+
+constexpr int KP = 16;            // kernel points padded to 16 in shared memory
+constexpr float SHADOW = 1e6f;    // blocks.py:277
+
+__global__ void kp_rowpos_kernel(const float* __restrict__ x, int ns, int cin, unsigned char* __restrict__ rowpos) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= ns) return;
+    float s = 0.f;
+    for (int c = lane; c < cin; c += 32) s += x[(size_t)warp * cin + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) rowpos[warp] = s > 0.0f;
+}
+
+__device__ __forceinline__ float kp_influence(float sq, float extent, int influence) {
+    if (influence == D3F_INFLUENCE_LINEAR) return fmaxf(1.0f - sqrtf(sq) / extent, 0.0f);
+    if (influence == D3F_INFLUENCE_GAUSSIAN) {
+        const float sigma = extent * 0.3f;
+        return expf(-sq / (2.0f * sigma * sigma + 1e-9f));
+    }
+    return 1.0f;
+}
+
+// d influence / d sq  (for the kernel-point gradient of deformable layers)
+__device__ __forceinline__ float kp_influence_grad(float sq, float w, float extent, int influence) {
+    if (influence == D3F_INFLUENCE_LINEAR) {
+        if (!(1.0f - sqrtf(sq) / extent >= 0.0f)) return 0.0f;
+        return -1.0f / (2.0f * extent * sqrtf(sq));
+    }
+    if (influence == D3F_INFLUENCE_GAUSSIAN) {
+        const float sigma = extent * 0.3f;
+        return -w / (2.0f * sigma * sigma + 1e-9f);
+    }
+    return 0.0f;
+}
+
+struct KpArgs {
+    const float* q; const float* s; const void* inds; long long ld; const float* x;
+    const float* kp; const float* mod; const unsigned char* rowpos;
+    int nq, ns, H, K, cin; float extent; int influence, aggregation;
+};
+
+// Phase 1 for one query (whole warp).  Fills w_s[h][KP] (0 for dropped / shadow neighbours),
+// idx_s[h] (-1 = skip), optionally rel_s[h][3]; returns the density count.
+template <bool IDX64, bool DEFORMED>
+__device__ __forceinline__ int kp_phase1(const KpArgs& a, int qi, int lane, const float* kp_s /*[KP*3]*/,
+                                         float* w_s, int* idx_s, float* rel_s, float* mind2 /*[KP] per lane or null*/) {
+    const float qx = a.q[3 * (size_t)qi], qy = a.q[3 * (size_t)qi + 1], qz = a.q[3 * (size_t)qi + 2];
+    const float ext2 = a.extent * a.extent;
+    int count = 0;
+    for (int h0 = 0; h0 < a.H; h0 += 32) {
+        const int h = h0 + lane;
+        bool pos = false;
+        if (h < a.H) {
+            long long idx = IDX64 ? ((const long long*)a.inds)[(size_t)qi * a.ld + h]
+                                  : (long long)((const int*)a.inds)[(size_t)qi * a.ld + h];
+            const bool valid = idx >= 0 && idx < a.ns;
+            float rx, ry, rz;
+            if (valid) {
+                rx = a.s[3 * idx] - qx; ry = a.s[3 * idx + 1] - qy; rz = a.s[3 * idx + 2] - qz;
+            } else {
+                rx = SHADOW - qx; ry = SHADOW - qy; rz = SHADOW - qz;
+            }
+            float wv[KP];
+            bool in_range = false;
+            float best = INFINITY; int best_k = 0;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                wv[k] = 0.f;
+                if (k < a.K) {
+                    const float dx = rx - kp_s[3 * k], dy = ry - kp_s[3 * k + 1], dz = rz - kp_s[3 * k + 2];
+                    const float sq = dx * dx + dy * dy + dz * dz;
+                    if (DEFORMED) {
+                        in_range |= sq < ext2;
+                        if (mind2) mind2[k] = fminf(mind2[k], sq);
+                    }
+                    if (sq < best) { best = sq; best_k = k; }
+                    wv[k] = kp_influence(sq, a.extent, a.influence);
+                }
+            }
+            if (a.aggregation == D3F_AGGREGATION_CLOSEST) {
+#pragma unroll
+                for (int k = 0; k < KP; ++k) if (k != best_k) wv[k] = 0.f;
+            }
+            const bool keep = valid && (!DEFORMED || in_range);
+            pos = keep && a.rowpos[idx];
+            idx_s[h] = keep ? (int)idx : -1;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) w_s[h * KP + k] = keep ? wv[k] : 0.f;
+            if (rel_s) { rel_s[3 * h] = rx; rel_s[3 * h + 1] = ry; rel_s[3 * h + 2] = rz; }
+        }
+        count += __popc(__ballot_sync(0xffffffffu, pos));
+    }
+    __syncwarp();
+    return count;
+}
+
+// per-warp shared memory: w_s[H*KP] | idx_s[H] | kp_s[KP*3] | rel_s[H*3] (backward only)
+__host__ __device__ inline size_t kp_warp_smem_floats(int H, bool with_rel) {
+    size_t f = (size_t)H * KP + H + KP * 3 + (with_rel ? (size_t)H * 3 : 0);
+    return (f + 3) & ~(size_t)3;
+}
+
+template <bool IDX64, bool DEFORMED, int CG>
+__global__ void __launch_bounds__(256)
+kp_correlate_kernel(KpArgs a, float* __restrict__ wf, float* __restrict__ wf_unmod, float* __restrict__ inv_n,
+                    float* __restrict__ min_d2) {
+    extern __shared__ float4 smem_f4[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qi = blockIdx.x * (blockDim.x >> 5) + warp;
+    float* base = (float*)smem_f4 + (size_t)warp * kp_warp_smem_floats(a.H, false);
+    float* w_s = base;
+    int* idx_s = (int*)(w_s + (size_t)a.H * KP);
+    float* kp_s = (float*)(idx_s + a.H);
+    if (qi >= a.nq) return;
+    for (int t = lane; t < KP * 3; t += 32) {
+        const int k = t / 3;
+        kp_s[t] = k < a.K ? (DEFORMED ? a.kp[(size_t)qi * a.K * 3 + t] : a.kp[t]) : 0.f;
+    }
+    __syncwarp();
+    float mind2[KP];
+    if (DEFORMED) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) mind2[k] = INFINITY;
+    }
+    const int count = kp_phase1<IDX64, DEFORMED>(a, qi, lane, kp_s, w_s, idx_s, nullptr,
+                                                 (DEFORMED && min_d2) ? mind2 : nullptr);
+    if (lane == 0) inv_n[qi] = 1.0f / (float)max(count, 1);
+    if (DEFORMED && min_d2) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            float v = mind2[k];
+            for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+            if (lane == 0 && k < a.K) min_d2[(size_t)qi * a.K + k] = v;
+        }
+    }
+    const float4* w4 = (const float4*)w_s;
+    for (int c0 = 0; c0 < a.cin; c0 += 32 * CG) {
+        float acc[CG][KP];
+#pragma unroll
+        for (int j = 0; j < CG; ++j)
+#pragma unroll
+            for (int k = 0; k < KP; ++k) acc[j][k] = 0.f;
+        for (int h = 0; h < a.H; ++h) {
+            const int idx = idx_s[h];
+            if (idx < 0) continue;
+            float xv[CG];
+#pragma unroll
+            for (int j = 0; j < CG; ++j) {
+                const int c = c0 + j * 32 + lane;
+                xv[j] = c < a.cin ? __ldg(&a.x[(size_t)idx * a.cin + c]) : 0.f;
+            }
+            float w[KP];
+#pragma unroll
+            for (int v = 0; v < KP / 4; ++v) {
+                const float4 t = w4[h * (KP / 4) + v];
+                w[4 * v] = t.x; w[4 * v + 1] = t.y; w[4 * v + 2] = t.z; w[4 * v + 3] = t.w;
+            }
+#pragma unroll
+            for (int j = 0; j < CG; ++j)
+#pragma unroll
+                for (int k = 0; k < KP; ++k) acc[j][k] = fmaf(w[k], xv[j], acc[j][k]);
+        }
+#pragma unroll
+        for (int j = 0; j < CG; ++j) {
+            const int c = c0 + j * 32 + lane;
+            if (c < a.cin) {
+#pragma unroll
+                for (int k = 0; k < KP; ++k)
+                    if (k < a.K) {
+                        float v = acc[j][k];
+                        const size_t o = ((size_t)qi * a.K + k) * a.cin + c;
+                        if (a.mod) {
+                            if (wf_unmod) wf_unmod[o] = v;
+                            v *= a.mod[(size_t)qi * a.K + k];
+                        }
+                        wf[o] = v;
+                    }
+            }
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// fp32 tiled GEMM.  C[M,N] (+)= rs[m] * sum_k opA(m,k) * ks[k] * opB(k,n)
+//   TA=false: opA(m,k)=A[m*lda+k]   TA=true: opA(m,k)=A[k*lda+m]
+//   TB=false: opB(k,n)=B[k*ldb+n]   TB=true: opB(k,n)=B[n*ldb+k]
+// gridDim.z > 1: split-K, partial tiles are atomically added into a pre-zeroed C.
+constexpr int GM = 64, GN = 64, GK = 16;
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+kp_gemm_kernel(int M, int N, int Kd, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+               float* __restrict__ C, int ldc, const float* __restrict__ rs, const float* __restrict__ ks,
+               int k_per_split) {
+    __shared__ float As[GK][GM + 4];
+    __shared__ float Bs[GK][GN + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
+    const int kbeg = blockIdx.z * k_per_split, kend = min(Kd, kbeg + k_per_split);
+    const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, 4x4 outputs each
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = kbeg; k0 < kend; k0 += GK) {
+        // A tile: GM x GK
+#pragma unroll
+        for (int r = 0; r < (GM * GK) / 256; ++r) {
+            const int e = tid + r * 256;
+            int m, k;
+            if (TA) { m = e % GM; k = e / GM; } else { k = e % GK; m = e / GK; }
+            const int gm = m0 + m, gk = k0 + k;
+            float v = 0.f;
+            if (gm < M && gk < kend) v = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+            As[k][m] = v;
+        }
+#pragma unroll
+        for (int r = 0; r < (GN * GK) / 256; ++r) {
+            const int e = tid + r * 256;
+            int n, k;
+            if (TB) { k = e % GK; n = e / GK; } else { n = e % GN; k = e / GN; }
+            const int gn = n0 + n, gk = k0 + k;
+            float v = 0.f;
+            if (gn < N && gk < kend) {
+                v = TB ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
+                if (ks) v *= ks[gk];
+            }
+            Bs[k][n] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < GK; ++k) {
+            const float4 av = *(const float4*)&As[k][ty * 4];
+            const float4 bv = *(const float4*)&Bs[k][tx * 4];
+            const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + ty * 4 + i;
+        if (gm >= M) continue;
+        const float sc = rs ? rs[gm] : 1.0f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + tx * 4 + j;
+            if (gn >= N) continue;
+            const float v = acc[i][j] * sc;
+            if (gridDim.z > 1) atomicAdd(&C[(size_t)gm * ldc + gn], v);
+            else C[(size_t)gm * ldc + gn] = v;
+        }
+    }
+}
+
+template <bool TA, bool TB>
+int kp_gemm(int M, int N, int Kd, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+            const float* rs, const float* ks, cudaStream_t stream) {
+    if (M <= 0 || N <= 0) return D3F_OK;
+    const int tiles = d3f_ceil_div(M, GM) * d3f_ceil_div(N, GN);
+    int splits = 1;
+    if (Kd > 0) {
+        // aim for >= 2 waves of 148 SMs x 2 CTAs when the output grid alone cannot fill the chip
+        const int target = 592;
+        if (tiles < target) splits = min(d3f_ceil_div(target, tiles), d3f_ceil_div(Kd, 4 * GK));
+        if (splits < 1) splits = 1;
+    }
+    int kps = d3f_ceil_div(d3f_ceil_div(Kd > 0 ? Kd : 1, splits), GK) * GK;
+    splits = d3f_ceil_div(Kd > 0 ? Kd : 1, kps);
+    if (splits > 1 || Kd == 0)
+        D3F_CHECK_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * ldc, stream));
+    if (Kd == 0) return D3F_OK;
+    dim3 grid(d3f_ceil_div(N, GN), d3f_ceil_div(M, GM), splits);
+    kp_gemm_kernel<TA, TB><<<grid, 256, 0, stream>>>(M, N, Kd, A, lda, B, ldb, C, ldc, rs, ks, kps);
+    D3F_CHECK_LAUNCH();
+    return D3F_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// backward scatter: dx[idx[i,h], c] += sum_k m[i,k] w[i,k,h] dwf[i,k,c]
+// deformed: also dkp[i,k,:] and (modulated) dmod[i,k] = sum_c dwf[i,k,c] * wf_unmod[i,k,c]
+template <bool IDX64, bool DEFORMED, int CG>
+__global__ void __launch_bounds__(256)
+kp_scatter_kernel(KpArgs a, const float* __restrict__ dwf, const float* __restrict__ wf_unmod,
+                  float* __restrict__ grad_x, float* __restrict__ grad_kp, float* __restrict__ grad_mod) {
+    extern __shared__ float4 smem_f4[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qi = blockIdx.x * (blockDim.x >> 5) + warp;
+    float* base = (float*)smem_f4 + (size_t)warp * kp_warp_smem_floats(a.H, true);
+    float* w_s = base;
+    int* idx_s = (int*)(w_s + (size_t)a.H * KP);
+    float* kp_s = (float*)(idx_s + a.H);
+    float* rel_s = kp_s + KP * 3;
+    if (qi >= a.nq) return;
+    for (int t = lane; t < KP * 3; t += 32) {
+        const int k = t / 3;
+        kp_s[t] = k < a.K ? (DEFORMED ? a.kp[(size_t)qi * a.K * 3 + t] : a.kp[t]) : 0.f;
+    }
+    __syncwarp();
+    kp_phase1<IDX64, DEFORMED>(a, qi, lane, kp_s, w_s, idx_s, rel_s, nullptr);
+    const float4* w4 = (const float4*)w_s;
+
+    float mk[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) mk[k] = (a.mod && k < a.K) ? a.mod[(size_t)qi * a.K + k] : 1.0f;
+
+    // t_hk accumulators for the kernel-point gradient: dkp[k] over this lane's channel slice
+    float gkp[KP][3];
+    float gmod[KP];
+    if (DEFORMED) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) { gkp[k][0] = gkp[k][1] = gkp[k][2] = 0.f; gmod[k] = 0.f; }
+    }
+
+    for (int c0 = 0; c0 < a.cin; c0 += 32 * CG) {
+        float d[CG][KP];
+#pragma unroll
+        for (int j = 0; j < CG; ++j) {
+            const int c = c0 + j * 32 + lane;
+#pragma unroll
+            for (int k = 0; k < KP; ++k)
+                d[j][k] = (k < a.K && c < a.cin) ? dwf[((size_t)qi * a.K + k) * a.cin + c] : 0.f;
+        }
+        if (DEFORMED && grad_mod && wf_unmod) {
+#pragma unroll
+            for (int j = 0; j < CG; ++j) {
+                const int c = c0 + j * 32 + lane;
+                if (c < a.cin)
+#pragma unroll
+                    for (int k = 0; k < KP; ++k)
+                        if (k < a.K) gmod[k] = fmaf(d[j][k], wf_unmod[((size_t)qi * a.K + k) * a.cin + c], gmod[k]);
+            }
+        }
+        for (int h = 0; h < a.H; ++h) {
+            const int idx = idx_s[h];
+            if (idx < 0) continue;
+            float w[KP];
+#pragma unroll
+            for (int v = 0; v < KP / 4; ++v) {
+                const float4 t = w4[h * (KP / 4) + v];
+                w[4 * v] = t.x; w[4 * v + 1] = t.y; w[4 * v + 2] = t.z; w[4 * v + 3] = t.w;
+            }
+            float xv[CG];
+            if (DEFORMED && grad_kp) {
+#pragma unroll
+                for (int j = 0; j < CG; ++j) {
+                    const int c = c0 + j * 32 + lane;
+                    xv[j] = c < a.cin ? __ldg(&a.x[(size_t)idx * a.cin + c]) : 0.f;
+                }
+            }
+            if (grad_x) {
+#pragma unroll
+                for (int j = 0; j < CG; ++j) {
+                    const int c = c0 + j * 32 + lane;
+                    float v = 0.f;
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) v = fmaf(w[k] * mk[k], d[j][k], v);
+                    if (c < a.cin) atomicAdd(&grad_x[(size_t)idx * a.cin + c], v);
+                }
+            }
+            if (DEFORMED && grad_kp) {
+                // dw[k] = m[k] * <dwf[k,:], x[idx,:]>   (this lane's channel slice; reduced over lanes at the end
+                // because d sq/d kp is lane-independent)
+                const float rx = rel_s[3 * h], ry = rel_s[3 * h + 1], rz = rel_s[3 * h + 2];
+                float best = INFINITY; int best_k = 0;
+                if (a.aggregation == D3F_AGGREGATION_CLOSEST) {
+#pragma unroll
+                    for (int k = 0; k < KP; ++k)
+                        if (k < a.K) {
+                            const float dx = rx - kp_s[3 * k], dy = ry - kp_s[3 * k + 1], dz = rz - kp_s[3 * k + 2];
+                            const float sq = dx * dx + dy * dy + dz * dz;
+                            if (sq < best) { best = sq; best_k = k; }
+                        }
+                }
+#pragma unroll
+                for (int k = 0; k < KP; ++k)
+                    if (k < a.K) {
+                        float t = 0.f;
+#pragma unroll
+                        for (int j = 0; j < CG; ++j) t = fmaf(d[j][k], xv[j], t);
+                        const float dx = rx - kp_s[3 * k], dy = ry - kp_s[3 * k + 1], dz = rz - kp_s[3 * k + 2];
+                        const float sq = dx * dx + dy * dy + dz * dz;
+                        float gw = kp_influence_grad(sq, w[k], a.extent, a.influence);
+                        if (a.aggregation == D3F_AGGREGATION_CLOSEST && k != best_k) gw = 0.f;
+                        const float f = t * mk[k] * gw * (-2.0f);
+                        gkp[k][0] = fmaf(f, dx, gkp[k][0]);
+                        gkp[k][1] = fmaf(f, dy, gkp[k][1]);
+                        gkp[k][2] = fmaf(f, dz, gkp[k][2]);
+                    }
+            }
+        }
+    }
+    if (DEFORMED) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            if (k >= a.K) continue;
+            if (grad_kp) {
+#pragma unroll
+                for (int ax = 0; ax < 3; ++ax) {
+                    float v = gkp[k][ax];
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == 0) grad_kp[((size_t)qi * a.K + k) * 3 + ax] = v;
+                }
+            }
+            if (grad_mod) {
+                float v = gmod[k];
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) grad_mod[(size_t)qi * a.K + k] = v;
+            }
+        }
+    }
+}
+
+int kp_warps_per_cta(int H, bool with_rel, size_t* smem) {
+    const size_t per = kp_warp_smem_floats(H, with_rel) * sizeof(float);
+    int warps = 8;
+    while (warps > 1 && per * warps > 160 * 1024) warps >>= 1;
+    *smem = per * warps;
+    return warps;
+}
+
+struct KpWs { unsigned char* rowpos; float* dwf; };
+size_t kp_layout(KpWs* w, void* base, size_t cap, int nq, int ns, int K, int cin) {
+    WsCursor c{(char*)base, 0, cap};
+    w->rowpos = c.take<unsigned char>((size_t)(ns > 0 ? ns : 1));
+    w->dwf = c.take<float>((size_t)(nq > 0 ? nq : 1) * K * cin);
+    return c.off;
+}
+
+int kp_check(int nq, int ns, int H, int K, int cin, int cout) {
+    D3F_REQUIRE(nq >= 0 && ns >= 0 && H >= 0 && cin >= 1 && cout >= 1, D3F_ERR_INVALID, "bad sizes");
+    D3F_REQUIRE(K >= 1 && K <= KP, D3F_ERR_UNSUPPORTED, "K must be in [1,16]");
+    D3F_REQUIRE(kp_warp_smem_floats(H, true) * sizeof(float) <= 160 * 1024, D3F_ERR_UNSUPPORTED,
+                "too many neighbour columns for one warp's shared memory");
+    return D3F_OK;
+}
+
+template <typename Kern>
+int kp_set_smem(Kern kern, size_t smem) {
+    if (smem > 48 * 1024)
+        D3F_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return D3F_OK;
+}
+
+#define KP_DISPATCH(NAME, IDX64, DEF, CG, ...)                                            \
+    do {                                                                                  \
+        auto kern = NAME<IDX64, DEF, CG>;                                                 \
+        int rc_ = kp_set_smem(kern, smem);                                                \
+        if (rc_) return rc_;                                                              \
+        kern<<<grid, warps * 32, smem, stream>>>(__VA_ARGS__);                            \
+    } while (0)
+
+#define KP_DISPATCH_ALL(NAME, ...)                                                        \
+    do {                                                                                  \
+        const int cg = cin <= 32 ? 1 : (cin <= 64 ? 2 : 4);                               \
+        if (idx_is_64) {                                                                  \
+            if (deformed) { if (cg == 1) KP_DISPATCH(NAME, true, true, 1, __VA_ARGS__);   \
+                            else if (cg == 2) KP_DISPATCH(NAME, true, true, 2, __VA_ARGS__); \
+                            else KP_DISPATCH(NAME, true, true, 4, __VA_ARGS__); }         \
+            else { if (cg == 1) KP_DISPATCH(NAME, true, false, 1, __VA_ARGS__);           \
+                   else if (cg == 2) KP_DISPATCH(NAME, true, false, 2, __VA_ARGS__);      \
+                   else KP_DISPATCH(NAME, true, false, 4, __VA_ARGS__); }                 \
+        } else {                                                                          \
+            if (deformed) { if (cg == 1) KP_DISPATCH(NAME, false, true, 1, __VA_ARGS__);  \
+                            else if (cg == 2) KP_DISPATCH(NAME, false, true, 2, __VA_ARGS__); \
+                            else KP_DISPATCH(NAME, false, true, 4, __VA_ARGS__); }        \
+            else { if (cg == 1) KP_DISPATCH(NAME, false, false, 1, __VA_ARGS__);          \
+                   else if (cg == 2) KP_DISPATCH(NAME, false, false, 2, __VA_ARGS__);     \
+                   else KP_DISPATCH(NAME, false, false, 4, __VA_ARGS__); }                \
+        }                                                                                 \
+    } while (0)
+
+}  // namespace
+
+extern "C" size_t d3f_kpconv_workspace_bytes(int n_queries, int n_supports, int n_neighbors, int K, int c_in,
+                                             int c_out) {
+    (void)n_neighbors; (void)c_out;
+    KpWs w;
+    return kp_layout(&w, nullptr, 0, n_queries, n_supports, K, c_in);
+}
+
+extern "C" int d3f_kpconv_forward(const float* q_pts, const float* s_pts, const void* inds, int idx_is_64,
+                                  int64_t ld_inds, const float* x, const float* weights,
+                                  const float* kernel_points, int deformed, const float* modulations,
+                                  int nq, int ns, int H, int K, int cin, int cout, float kp_extent, int influence,
+                                  int aggregation, float* out, float* wf, float* wf_unmod, float* inv_n,
+                                  float* min_d2, void* workspace, size_t workspace_bytes, d3f_stream stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = kp_check(nq, ns, H, K, cin, cout);
+    if (rc) return rc;
+    if (nq == 0) return D3F_OK;
+    D3F_REQUIRE(q_pts && s_pts && (inds || H == 0) && x && weights && kernel_points && out && wf && inv_n,
+                D3F_ERR_INVALID, "null pointer");
+    D3F_REQUIRE(!modulations || wf_unmod, D3F_ERR_INVALID, "wf_unmod is required with modulations");
+    D3F_REQUIRE(influence >= 0 && influence <= 2 && aggregation >= 0 && aggregation <= 1, D3F_ERR_INVALID, "bad mode");
+    KpWs w;
+    const size_t need = kp_layout(&w, workspace, workspace_bytes, nq, ns, K, cin);
+    D3F_REQUIRE(workspace && need <= workspace_bytes, D3F_ERR_WORKSPACE, "workspace too small");
+    if (ns > 0) {
+        kp_rowpos_kernel<<<d3f_ceil_div(ns, 8), 256, 0, stream>>>(x, ns, cin, w.rowpos);
+        D3F_CHECK_LAUNCH();
+    }
+    KpArgs a{q_pts, s_pts, inds, (long long)ld_inds, x, kernel_points, modulations, w.rowpos,
+             nq, ns, H, K, cin, kp_extent, influence, aggregation};
+    size_t smem;
+    const int warps = kp_warps_per_cta(H, false, &smem);
+    const int grid = d3f_ceil_div(nq, warps);
+    KP_DISPATCH_ALL(kp_correlate_kernel, a, wf, wf_unmod, inv_n, deformed ? min_d2 : nullptr);
+    D3F_CHECK_LAUNCH();
+    return kp_gemm<false, false>(nq, cout, K * cin, wf, K * cin, weights, cout, out, cout, inv_n, nullptr, stream);
+}
+
+extern "C" int d3f_kpconv_backward(const float* q_pts, const float* s_pts, const void* inds, int idx_is_64,
+                                   int64_t ld_inds, const float* x, const float* weights,
+                                   const float* kernel_points, int deformed, const float* modulations,
+                                   int nq, int ns, int H, int K, int cin, int cout, float kp_extent,
+                                   int influence, int aggregation, const float* wf, const float* wf_unmod,
+                                   const float* inv_n, const float* grad_out, float* grad_x,
+                                   float* grad_weights, float* grad_kernel_points, float* grad_modulations,
+                                   void* workspace, size_t workspace_bytes, d3f_stream stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = kp_check(nq, ns, H, K, cin, cout);
+    if (rc) return rc;
+    D3F_REQUIRE(influence >= 0 && influence <= 2 && aggregation >= 0 && aggregation <= 1, D3F_ERR_INVALID, "bad mode");
+    if (grad_x && ns > 0) D3F_CHECK_CUDA(cudaMemsetAsync(grad_x, 0, sizeof(float) * (size_t)ns * cin, stream));
+    if (nq == 0) {
+        if (grad_weights) D3F_CHECK_CUDA(cudaMemsetAsync(grad_weights, 0, sizeof(float) * (size_t)K * cin * cout, stream));
+        return D3F_OK;
+    }
+    D3F_REQUIRE(q_pts && s_pts && (inds || H == 0) && x && weights && kernel_points && wf && inv_n && grad_out,
+                D3F_ERR_INVALID, "null pointer");
+    KpWs w;
+    const size_t need = kp_layout(&w, workspace, workspace_bytes, nq, ns, K, cin);
+    D3F_REQUIRE(workspace && need <= workspace_bytes, D3F_ERR_WORKSPACE, "workspace too small");
+    const int KC = K * cin;
+    // dW[kc, o] = sum_i wf[i, kc] * inv_n[i] * g[i, o]
+    if (grad_weights) {
+        rc = kp_gemm<true, false>(KC, cout, nq, wf, KC, grad_out, cout, grad_weights, cout, nullptr, inv_n, stream);
+        if (rc) return rc;
+    }
+    const bool need_scatter = grad_x || (deformed && (grad_kernel_points || grad_modulations));
+    if (!need_scatter) return D3F_OK;
+    // dwf[i, kc] = inv_n[i] * sum_o g[i, o] * W[kc, o]
+    rc = kp_gemm<false, true>(nq, KC, cout, grad_out, cout, weights, cout, w.dwf, KC, inv_n, nullptr, stream);
+    if (rc) return rc;
+    if (ns > 0) {
+        kp_rowpos_kernel<<<d3f_ceil_div(ns, 8), 256, 0, stream>>>(x, ns, cin, w.rowpos);
+        D3F_CHECK_LAUNCH();
+    }
+    KpArgs a{q_pts, s_pts, inds, (long long)ld_inds, x, kernel_points, modulations, w.rowpos,
+             nq, ns, H, K, cin, kp_extent, influence, aggregation};
+    size_t smem;
+    const int warps = kp_warps_per_cta(H, true, &smem);
+    const int grid = d3f_ceil_div(nq, warps);
+    KP_DISPATCH_ALL(kp_scatter_kernel, a, w.dwf, wf_unmod, grad_x, deformed ? grad_kernel_points : nullptr,
+                    deformed ? grad_modulations : nullptr);
+    D3F_CHECK_LAUNCH();
+    return D3F_OK;
+}

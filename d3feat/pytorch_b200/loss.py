@@ -1,0 +1,139 @@
+"""Descriptor / detector losses -- drop-in for utils/loss.py of the reference, computed by the
+sm_100a pair-loss kernels (d3f_pair_loss_forward / _backward).
+
+``CircleLoss``, ``ContrastiveLoss`` and ``DetLoss`` keep the reference signatures and return
+values (loss.py:111-141, 55-97, 149-158).  ``PairLoss`` is the fused form of the trainer wiring
+(trainer.py:96-98): descriptor loss + detector loss in one forward/backward, no host sync.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def cdist(a, b, metric='euclidean'):
+    """Pairwise distance matrix with the reference's metrics (loss.py:8-44).  Forward only."""
+    if metric not in ops.METRIC:
+        raise NotImplementedError('The following metric is not implemented by `cdist` yet: {}'.format(metric))
+    return ops.pair_dist(a, b, metric)
+
+
+class _PairLossFunction(torch.autograd.Function):
+    """(anchor, positive, anc_score, pos_score) -> (desc_loss, det_loss, dists, accuracy, furthest_pos, avg_neg)."""
+
+    @staticmethod
+    def forward(ctx, anchor, positive, anc_score, pos_score, dist_keypts, kind, metric, safe_radius, pos_margin,
+                neg_margin, log_scale):
+        dists, stats, fp, an, aux, saved = ops.pair_loss_forward(anchor, positive, dist_keypts, anc_score, pos_score,
+                                                                 kind, metric, safe_radius, pos_margin, neg_margin,
+                                                                 log_scale)
+        ctx.set_materialize_grads(False)
+        ctx.saved = saved
+        ctx.aux, ctx.dists_saved = aux, dists
+        ctx.cfg = (kind, metric, safe_radius, pos_margin, neg_margin, log_scale)
+        ctx.score_shapes = (None if anc_score is None else anc_score.shape,
+                            None if pos_score is None else pos_score.shape)
+        acc = stats[2].clone()
+        ctx.mark_non_differentiable(acc, fp, an)
+        return stats[0].clone(), stats[1].clone(), dists, acc, fp, an
+
+    @staticmethod
+    def backward(ctx, g_desc, g_det, g_dists, _a, _b, _c):
+        if g_dists is not None:
+            raise RuntimeError("the `dists` output of the fused pair loss only feeds DetLoss inside the kernel; "
+                               "use PairLoss (or DetLoss on it) rather than differentiating it directly")
+        gl = torch.stack([g_desc if g_desc is not None else torch.zeros((), device=ctx.aux.device),
+                          g_det if g_det is not None else torch.zeros((), device=ctx.aux.device)]).float()
+        kind, metric, safe_radius, pm, nm, ls = ctx.cfg
+        ga, gp, gsa, gsp = ops.pair_loss_backward(ctx.saved, kind, metric, safe_radius, pm, nm, ls,
+                                                  ctx.dists_saved, ctx.aux, gl)
+        sa_shape, sp_shape = ctx.score_shapes
+        gsa = gsa.reshape(sa_shape) if gsa is not None else None
+        gsp = gsp.reshape(sp_shape) if gsp is not None else None
+        return ga, gp, gsa, gsp, None, None, None, None, None, None, None
+
+
+class PairLoss(nn.Module):
+    """Descriptor loss ('circle' | 'contrastive') + detector loss on its distance matrix, fused.
+
+    forward(anchor [P,D], positive [P,D], dist_keypts [P,P], anc_score [P,1], pos_score [P,1])
+      -> dict(desc_loss, det_loss, accuracy, dists, furthest_positive, average_negative)   (device tensors)
+    """
+
+    def __init__(self, desc_loss='circle', dist_type='euclidean', log_scale=10, safe_radius=0.10, pos_margin=0.1,
+                 neg_margin=1.4):
+        super().__init__()
+        self.kind, self.metric = desc_loss, dist_type
+        self.log_scale, self.safe_radius = log_scale, safe_radius
+        self.pos_margin, self.neg_margin = pos_margin, neg_margin
+
+    def forward(self, anchor, positive, dist_keypts, anc_score=None, pos_score=None):
+        desc, det, dists, acc, fp, an = _PairLossFunction.apply(
+            anchor, positive, anc_score, pos_score, dist_keypts, self.kind, self.metric, self.safe_radius,
+            self.pos_margin, self.neg_margin, self.log_scale)
+        return dict(desc_loss=desc, det_loss=det, accuracy=acc, dists=dists, furthest_positive=fp,
+                    average_negative=an)
+
+
+def _tag(dists, **meta):
+    """Remember the inputs `dists` was computed from, so that DetLoss(dists, ...) can run the fused
+    kernel: detector gradients then reach the descriptors, as they do through the reference's
+    un-detached `dists` (loss.py:141 / trainer.py:96-97)."""
+    dists = dists.detach()
+    dists._d3f_meta = meta
+    return dists
+
+
+class CircleLoss(nn.Module):
+    def __init__(self, dist_type='cosine', log_scale=10, safe_radius=0.10, pos_margin=0.1, neg_margin=1.4):
+        super().__init__()
+        self.log_scale = log_scale
+        self.pos_margin = pos_margin
+        self.neg_margin = neg_margin
+        self.pos_optimal = pos_margin
+        self.neg_optimal = neg_margin
+        self.dist_type = dist_type
+        self.safe_radius = safe_radius
+        self._kind = 'circle'
+
+    def forward(self, anchor, positive, dist_keypts):
+        desc, _det, dists, acc, fp, an = _PairLossFunction.apply(
+            anchor, positive, None, None, dist_keypts, self._kind, self.dist_type, self.safe_radius,
+            self.pos_margin, self.neg_margin, self.log_scale)
+        dists = _tag(dists, anchor=anchor, positive=positive, dist_keypts=dist_keypts, kind=self._kind,
+                     metric=self.dist_type, safe_radius=self.safe_radius, pos_margin=self.pos_margin,
+                     neg_margin=self.neg_margin, log_scale=self.log_scale)
+        return desc, acc, fp.tolist(), an.tolist(), 0, dists
+
+
+class ContrastiveLoss(nn.Module):
+    def __init__(self, pos_margin=0.1, neg_margin=1.4, metric='euclidean', safe_radius=0.25):
+        super().__init__()
+        self.pos_margin = pos_margin
+        self.neg_margin = neg_margin
+        self.metric = metric
+        self.safe_radius = safe_radius
+
+    def forward(self, anchor, positive, dist_keypts):
+        desc, _det, dists, acc, fp, an = _PairLossFunction.apply(
+            anchor, positive, None, None, dist_keypts, 'contrastive', self.metric, self.safe_radius,
+            self.pos_margin, self.neg_margin, 10.0)
+        dists = _tag(dists, anchor=anchor, positive=positive, dist_keypts=dist_keypts, kind='contrastive',
+                     metric=self.metric, safe_radius=self.safe_radius, pos_margin=self.pos_margin,
+                     neg_margin=self.neg_margin, log_scale=10.0)
+        return desc, acc, fp.tolist(), an.tolist(), 0, dists
+
+
+class DetLoss(nn.Module):
+    def __init__(self, metric='euclidean'):
+        super().__init__()
+        self.metric = metric
+
+    def forward(self, dists, anc_score, pos_score):
+        meta = getattr(dists, '_d3f_meta', None)
+        if meta is None:
+            raise RuntimeError("DetLoss expects the `dists` returned by this package's CircleLoss/ContrastiveLoss")
+        _desc, det, *_ = _PairLossFunction.apply(
+            meta['anchor'], meta['positive'], anc_score, pos_score, meta['dist_keypts'], meta['kind'],
+            meta['metric'], meta['safe_radius'], meta['pos_margin'], meta['neg_margin'], meta['log_scale'])
+        return det

@@ -1,0 +1,230 @@
+"""Tensor-level wrappers over the C ABI (include/d3feat_b200.h).
+
+torch is used for device memory and streams only: every function allocates its outputs
+and workspace with torch, passes raw device pointers plus the current CUDA stream to
+libd3feat_b200.so, and returns torch tensors.  No function here has a CPU path.
+"""
+import torch
+
+from . import _lib
+
+INFLUENCE = {"constant": 0, "linear": 1, "gaussian": 2}
+AGGREGATION = {"sum": 0, "closest": 1}
+METRIC = {"euclidean": 0, "sqeuclidean": 1, "cityblock": 2, "cosine": 3, "arccosine": 4}
+LOSS_KIND = {"circle": 0, "contrastive": 1}
+
+launch_count = 0  # number of C-ABI hot-path calls issued (bench.py reports kernel launches from ncu)
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _cuda_f32(t, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RuntimeError("d3feat.pytorch_b200: `%s` must be a CUDA tensor (there is no CPU path)" % name)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _pow2ceil(v):
+    p = 1
+    while p < v:
+        p <<= 1
+    return p
+
+
+# --------------------------------------------------------------------------- radius neighbours
+def radius_neighbors_raw(queries, supports, q_len, s_len, radius, max_cols, index_dtype=torch.int64,
+                         row_capacity=None, count_only=False):
+    """One call of d3f_radius_neighbors.  Returns (idx [Nq,max_cols] or None, info int32[4] on device)."""
+    lib = _lib.load()
+    queries, supports = _cuda_f32(queries, "queries"), _cuda_f32(supports, "supports")
+    dev = queries.device
+    q_len = q_len.to(device=dev, dtype=torch.int32).contiguous()
+    s_len = s_len.to(device=dev, dtype=torch.int32).contiguous()
+    nq, ns, nb = queries.shape[0], supports.shape[0], q_len.shape[0]
+    info = torch.empty(4, dtype=torch.int32, device=dev)
+    if row_capacity is None:
+        row_capacity = min(8192, max(64, _pow2ceil(2 * max(int(max_cols), 1))))
+    out = None
+    if not count_only:
+        out = torch.empty((nq, int(max_cols)), dtype=index_dtype, device=dev)
+    ws_bytes = lib.d3f_radius_neighbors_workspace_bytes(nq, ns, nb)
+    ws = _ws(ws_bytes, dev)
+    global launch_count
+    launch_count += 1
+    _lib.check(lib.d3f_radius_neighbors(_p(queries), _p(supports), _p(q_len), _p(s_len), nb, nq, ns,
+                                        float(radius), int(max_cols) if not count_only else 0, _p(out),
+                                        1 if index_dtype == torch.int64 else 0, _p(info), int(row_capacity),
+                                        _p(ws), ws.numel(), _stream()))
+    return out, info
+
+
+def radius_neighbors(queries, supports, q_len, s_len, radius, max_neighbors=0, index_dtype=torch.int64):
+    """Drop-in semantics of batch_neighbors_kpconv (datasets/dataloader.py:52-67): the matrix has
+    min(max_count, max_neighbors) columns (all of them if max_neighbors <= 0).  Reads 2 ints back
+    from the device to learn the width, exactly the information the reference gets from the shape
+    of the NumPy array."""
+    if max_neighbors <= 0:
+        _, info = radius_neighbors_raw(queries, supports, q_len, s_len, radius, 0, index_dtype, 64, count_only=True)
+        max_neighbors = max(int(info[0].item()), 1)
+    cap = None
+    while True:
+        out, info = radius_neighbors_raw(queries, supports, q_len, s_len, radius, max_neighbors, index_dtype, cap)
+        h = info[:2].tolist()
+        if h[1] == 0:
+            break
+        if h[0] > 8192:
+            raise _lib.D3FError("a query has %d in-range supports; more than the 8192-entry row buffer" % h[0])
+        cap = _pow2ceil(h[0])  # a row overflowed the candidate buffer: redo with room for the largest row
+    width = min(h[0], int(max_neighbors))
+    return out[:, :width].contiguous() if width < out.shape[1] else out
+
+
+# --------------------------------------------------------------------------- grid subsampling
+def grid_subsample(points, lengths, sample_dl):
+    """Drop-in semantics of batch_grid_subsampling_kpconv (datasets/dataloader.py:12-21), points only.
+    Returns (s_points [M,3] f32, s_len [B] i32) on the device; reads B ints back to size s_points."""
+    lib = _lib.load()
+    points = _cuda_f32(points, "points")
+    dev = points.device
+    lengths = lengths.to(device=dev, dtype=torch.int32).contiguous()
+    n, nb = points.shape[0], lengths.shape[0]
+    out = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    out_len = torch.empty(nb, dtype=torch.int32, device=dev)
+    ws = _ws(lib.d3f_grid_subsample_workspace_bytes(n, nb), dev)
+    global launch_count
+    launch_count += 1
+    _lib.check(lib.d3f_grid_subsample(_p(points), _p(lengths), nb, n, float(sample_dl), _p(out), _p(out_len),
+                                      _p(ws), ws.numel(), _stream()))
+    host_len = out_len.tolist()
+    if any(v < 0 for v in host_len):
+        raise _lib.D3FError("grid_subsample: voxel grid exceeds the supported key range (code %s)" % host_len)
+    return out[:sum(host_len)], out_len
+
+
+# --------------------------------------------------------------------------- KPConv
+def kpconv_forward(q_pts, s_pts, inds, x, weights, kernel_points, extent, influence, aggregation,
+                   deformed=False, modulations=None, want_min_d2=False):
+    lib = _lib.load()
+    q_pts, s_pts, x = _cuda_f32(q_pts, "q_pts"), _cuda_f32(s_pts, "s_pts"), _cuda_f32(x, "x")
+    weights, kernel_points = _cuda_f32(weights, "weights"), _cuda_f32(kernel_points, "kernel_points")
+    if not inds.is_cuda:
+        raise RuntimeError("d3feat.pytorch_b200: `neighb_inds` must be a CUDA tensor")
+    if inds.dtype not in (torch.int32, torch.int64):
+        inds = inds.long()
+    if inds.stride(-1) != 1:
+        inds = inds.contiguous()
+    dev = x.device
+    nq, ns, H = q_pts.shape[0], s_pts.shape[0], inds.shape[1]
+    K, cin, cout = weights.shape
+    if x.shape[0] != ns or x.shape[1] != cin:
+        raise RuntimeError("KPConv: x must be [n_supports, in_channels] = [%d, %d], got %s" % (ns, cin, tuple(x.shape)))
+    out = torch.empty((nq, cout), dtype=torch.float32, device=dev)
+    wf = torch.empty((nq, K, cin), dtype=torch.float32, device=dev)
+    wf_un = torch.empty_like(wf) if modulations is not None else None
+    inv_n = torch.empty(nq, dtype=torch.float32, device=dev)
+    min_d2 = torch.empty((nq, K), dtype=torch.float32, device=dev) if (deformed and want_min_d2) else None
+    if modulations is not None:
+        modulations = _cuda_f32(modulations, "modulations")
+    ws = _ws(lib.d3f_kpconv_workspace_bytes(nq, ns, H, K, cin, cout), dev)
+    global launch_count
+    launch_count += 1
+    _lib.check(lib.d3f_kpconv_forward(_p(q_pts), _p(s_pts), _p(inds), 1 if inds.dtype == torch.int64 else 0,
+                                      inds.stride(0) if H > 0 else 0, _p(x), _p(weights), _p(kernel_points),
+                                      1 if deformed else 0, _p(modulations), nq, ns, H, K, cin, cout,
+                                      float(extent), INFLUENCE[influence], AGGREGATION[aggregation],
+                                      _p(out), _p(wf), _p(wf_un), _p(inv_n), _p(min_d2), _p(ws), ws.numel(), _stream()))
+    return out, wf, wf_un, inv_n, min_d2
+
+
+def kpconv_backward(q_pts, s_pts, inds, x, weights, kernel_points, extent, influence, aggregation, deformed,
+                    modulations, wf, wf_un, inv_n, grad_out, need_x, need_w, need_kp, need_mod):
+    lib = _lib.load()
+    dev = x.device
+    nq, ns, H = q_pts.shape[0], s_pts.shape[0], inds.shape[1]
+    K, cin, cout = weights.shape
+    grad_out = _cuda_f32(grad_out, "grad_out")
+    gx = torch.empty((ns, cin), dtype=torch.float32, device=dev) if need_x else None
+    gw = torch.empty_like(weights) if need_w else None
+    gkp = torch.empty((nq, K, 3), dtype=torch.float32, device=dev) if (need_kp and deformed) else None
+    gmod = torch.empty((nq, K), dtype=torch.float32, device=dev) if (need_mod and modulations is not None) else None
+    ws = _ws(lib.d3f_kpconv_workspace_bytes(nq, ns, H, K, cin, cout), dev)
+    global launch_count
+    launch_count += 1
+    _lib.check(lib.d3f_kpconv_backward(_p(q_pts), _p(s_pts), _p(inds), 1 if inds.dtype == torch.int64 else 0,
+                                       inds.stride(0) if H > 0 else 0, _p(x), _p(weights), _p(kernel_points),
+                                       1 if deformed else 0, _p(modulations), nq, ns, H, K, cin, cout,
+                                       float(extent), INFLUENCE[influence], AGGREGATION[aggregation],
+                                       _p(wf), _p(wf_un), _p(inv_n), _p(grad_out), _p(gx), _p(gw), _p(gkp), _p(gmod),
+                                       _p(ws), ws.numel(), _stream()))
+    return gx, gw, gkp, gmod
+
+
+# --------------------------------------------------------------------------- descriptor distance / losses
+def pair_dist(a, b, metric="euclidean"):
+    lib = _lib.load()
+    a, b = _cuda_f32(a, "a"), _cuda_f32(b, "b")
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+    global launch_count
+    launch_count += 1
+    _lib.check(lib.d3f_pair_dist(_p(a), _p(b), a.shape[0], b.shape[0], a.shape[1], METRIC[metric], _p(out), _stream()))
+    return out
+
+
+def _keypts(dist_keypts, dev):
+    if not dist_keypts.is_cuda:
+        dist_keypts = dist_keypts.to(dev)
+    if dist_keypts.dtype not in (torch.float32, torch.float64):
+        dist_keypts = dist_keypts.double()
+    return dist_keypts.contiguous()
+
+
+def pair_loss_forward(anchor, positive, dist_keypts, anc_score, pos_score, kind, metric, safe_radius,
+                      pos_margin, neg_margin, log_scale):
+    lib = _lib.load()
+    anchor, positive = _cuda_f32(anchor, "anchor"), _cuda_f32(positive, "positive")
+    dev = anchor.device
+    P, D = anchor.shape
+    dk = _keypts(dist_keypts, dev)
+    sa = _cuda_f32(anc_score.reshape(-1), "anc_score") if anc_score is not None else None
+    sp = _cuda_f32(pos_score.reshape(-1), "pos_score") if pos_score is not None else None
+    dists = torch.empty((P, P), dtype=torch.float32, device=dev)
+    stats = torch.empty(8, dtype=torch.float32, device=dev)
+    fp = torch.empty(P, dtype=torch.float32, device=dev)
+    an = torch.empty(P, dtype=torch.float32, device=dev)
+    aux = torch.empty(lib.d3f_pair_loss_aux_floats(P), dtype=torch.float32, device=dev)
+    global launch_count
+    launch_count += 1
+    _lib.check(lib.d3f_pair_loss_forward(_p(anchor), _p(positive), P, D, _p(dk), 1 if dk.dtype == torch.float64 else 0,
+                                         _p(sa), _p(sp), LOSS_KIND[kind], METRIC[metric], float(safe_radius),
+                                         float(pos_margin), float(neg_margin), float(log_scale),
+                                         _p(dists), _p(stats), _p(fp), _p(an), _p(aux), _stream()))
+    return dists, stats, fp, an, aux, (anchor, positive, dk, sa, sp)
+
+
+def pair_loss_backward(saved, kind, metric, safe_radius, pos_margin, neg_margin, log_scale, dists, aux, grad_losses):
+    lib = _lib.load()
+    anchor, positive, dk, sa, sp = saved
+    P, D = anchor.shape
+    ga, gp = torch.empty_like(anchor), torch.empty_like(positive)
+    gsa = torch.empty_like(sa) if sa is not None else None
+    gsp = torch.empty_like(sp) if sp is not None else None
+    global launch_count
+    launch_count += 1
+    _lib.check(lib.d3f_pair_loss_backward(_p(anchor), _p(positive), P, D, _p(dk), 1 if dk.dtype == torch.float64 else 0,
+                                          _p(sa), _p(sp), LOSS_KIND[kind], METRIC[metric], float(safe_radius),
+                                          float(pos_margin), float(neg_margin), float(log_scale),
+                                          _p(dists), _p(aux), _p(grad_losses.contiguous()), _p(ga), _p(gp), _p(gsa), _p(gsp),
+                                          _stream()))
+    return ga, gp, gsa, gsp

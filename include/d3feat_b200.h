@@ -1,0 +1,165 @@
+/*
+ * d3feat_b200.h -- C ABI of libd3feat_b200.so: the B200 (sm_100a) implementation of
+ * D3Feat's data-parallel hot path.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions:
+ *   - every array pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns every buffer (outputs and workspace); no entry point allocates
+ *     device memory or synchronises the device; all work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*);
+ *   - all matrices are dense row-major; indices are int32 or int64 as flagged;
+ *   - return value: D3F_OK (0) or a negative d3f_status; d3f_last_error_string()
+ *     describes the last failure on the calling thread;
+ *   - thread-safe for calls that use distinct streams and distinct buffers.
+ *
+ * Each entry point cites the reference interface it replaces (file:line under the
+ * XuyangBai/D3Feat.pytorch tree).  INTEGRATION.md shows the reference-side binding.
+ */
+#ifndef D3FEAT_B200_H
+#define D3FEAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* d3f_stream; /* cudaStream_t */
+
+typedef enum {
+    D3F_OK = 0,
+    D3F_ERR_INVALID = -1,     /* bad argument (null pointer, negative size, unknown mode) */
+    D3F_ERR_CUDA = -2,        /* a CUDA runtime call failed; see d3f_last_error_string() */
+    D3F_ERR_WORKSPACE = -3,   /* workspace smaller than *_workspace_bytes() */
+    D3F_ERR_UNSUPPORTED = -4  /* shape outside what the kernels implement */
+} d3f_status;
+
+/* influence / aggregation / metric / loss selectors (values of the reference's config strings) */
+enum { D3F_INFLUENCE_CONSTANT = 0, D3F_INFLUENCE_LINEAR = 1, D3F_INFLUENCE_GAUSSIAN = 2 }; /* blocks.py:329-343 */
+enum { D3F_AGGREGATION_SUM = 0, D3F_AGGREGATION_CLOSEST = 1 };                             /* blocks.py:346-351 */
+enum { D3F_METRIC_EUCLIDEAN = 0, D3F_METRIC_SQEUCLIDEAN = 1, D3F_METRIC_CITYBLOCK = 2,
+       D3F_METRIC_COSINE = 3, D3F_METRIC_ARCCOSINE = 4 };                                  /* loss.py:8-44 */
+enum { D3F_LOSS_CIRCLE = 0, D3F_LOSS_CONTRASTIVE = 1 };                                    /* loss.py:47,100 */
+
+int d3f_version(void);
+const char* d3f_last_error_string(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Radius neighbours.  Replaces radius_neighbors.batch_query
+ * (cpp_wrappers/cpp_neighbors/wrapper.cpp:58-238 -> neighbors/neighbors.cpp:211-332), called
+ * from datasets/dataloader.py:63.
+ *
+ * For every query, all supports OF THE SAME BATCH ELEMENT with fp32 d2 < radius*radius
+ * (d2 = (dx*dx + dy*dy) + dz*dz, no FMA), ordered by ascending (d2, index); indices are global
+ * rows of `supports`; rows are padded with n_supports.  Only the first `max_cols` neighbours of
+ * a row are written (dataloader.py:64-65 truncation).
+ *
+ *   queries   [n_queries,3] f32     supports [n_supports,3] f32
+ *   q_lengths [n_batch] i32         s_lengths [n_batch] i32      (device)
+ *   out_idx   [n_queries,max_cols] i32 (idx_is_64=0) or i64 (idx_is_64=1); may be NULL: count only
+ *   out_info  [4] i32 (device): [0] = max neighbour count over all queries BEFORE truncation
+ *             (the reference's matrix width, neighbors.cpp:300), [1] = 1 if some row had more
+ *             than `row_capacity` in-range supports (its selection is then incomplete: retry with a
+ *             larger capacity), [2] = number of occupied grid cells, [3] reserved.
+ *   row_capacity: per-query candidate buffer (power of two, 64..8192).
+ */
+size_t d3f_radius_neighbors_workspace_bytes(int n_queries, int n_supports, int n_batch);
+int d3f_radius_neighbors(const float* queries, const float* supports,
+                         const int32_t* q_lengths, const int32_t* s_lengths, int n_batch,
+                         int n_queries, int n_supports, float radius, int max_cols,
+                         void* out_idx, int idx_is_64, int32_t* out_info, int row_capacity,
+                         void* workspace, size_t workspace_bytes, d3f_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Grid subsampling (barycentre per occupied voxel, points only).  Replaces
+ * grid_subsampling.subsample_batch (cpp_wrappers/cpp_subsampling/wrapper.cpp:62-333 ->
+ * grid_subsampling/grid_subsampling.cpp:109-211), called from datasets/dataloader.py:17.
+ * Output values AND order are bit-identical to the reference, i.e. the iteration order of
+ * libstdc++'s std::unordered_map<size_t,SampledData> (grid_subsampling.cpp:48,85).
+ *
+ *   points [n_points,3] f32, lengths [n_batch] i32 (device)
+ *   out_points  [n_points,3] f32 capacity; the first sum(out_lengths) rows are valid
+ *   out_lengths [n_batch] i32 (device)
+ */
+size_t d3f_grid_subsample_workspace_bytes(int n_points, int n_batch);
+int d3f_grid_subsample(const float* points, const int32_t* lengths, int n_batch, int n_points,
+                       float sample_dl, float* out_points, int32_t* out_lengths,
+                       void* workspace, size_t workspace_bytes, d3f_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * KPConv.  Replaces the ATen op chain of KPConv.forward (models/blocks.py:237-382) and its
+ * autograd backward.
+ *
+ *   q_pts [Nq,3], s_pts [Ns,3], inds [Nq,H] (i32 or i64, row stride ld_inds elements, value Ns =
+ *   shadow neighbour), x [Ns,Cin], weights [K,Cin,Cout], kernel_points [K,3] (rigid) or
+ *   [Nq,K,3] (deformed != 0: blocks.py:286-291, which also enables the in-range neighbour filter
+ *   of blocks.py:300-324), modulations [Nq,K] or NULL (blocks.py:365-366).
+ *
+ * forward outputs:
+ *   out [Nq,Cout]; wf [Nq,K,Cin] = kernel-point-weighted neighbour features after modulation
+ *   (the [n_points,n_kpoints,in_fdim] tensor of blocks.py:362-366; saved for backward);
+ *   wf_unmod [Nq,K,Cin] or NULL (required iff modulations != NULL: wf before modulation);
+ *   inv_n [Nq] = 1 / max(1, #neighbours with positive feature sum) (blocks.py:377-380);
+ *   min_d2 [Nq,K] or NULL (deformed only, blocks.py:303).
+ */
+size_t d3f_kpconv_workspace_bytes(int n_queries, int n_supports, int n_neighbors, int K, int c_in, int c_out);
+int d3f_kpconv_forward(const float* q_pts, const float* s_pts, const void* inds, int idx_is_64,
+                       int64_t ld_inds, const float* x, const float* weights,
+                       const float* kernel_points, int deformed, const float* modulations,
+                       int n_queries, int n_supports, int n_neighbors, int K, int c_in, int c_out,
+                       float kp_extent, int influence, int aggregation,
+                       float* out, float* wf, float* wf_unmod, float* inv_n, float* min_d2,
+                       void* workspace, size_t workspace_bytes, d3f_stream stream);
+
+/* backward: grad_out [Nq,Cout] ->
+ *   grad_x [Ns,Cin] or NULL (fully overwritten), grad_weights [K,Cin,Cout] or NULL (overwritten),
+ *   grad_kernel_points [Nq,K,3] or NULL (deformed only), grad_modulations [Nq,K] or NULL. */
+int d3f_kpconv_backward(const float* q_pts, const float* s_pts, const void* inds, int idx_is_64,
+                        int64_t ld_inds, const float* x, const float* weights,
+                        const float* kernel_points, int deformed, const float* modulations,
+                        int n_queries, int n_supports, int n_neighbors, int K, int c_in, int c_out,
+                        float kp_extent, int influence, int aggregation,
+                        const float* wf, const float* wf_unmod, const float* inv_n,
+                        const float* grad_out,
+                        float* grad_x, float* grad_weights, float* grad_kernel_points,
+                        float* grad_modulations,
+                        void* workspace, size_t workspace_bytes, d3f_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Pairwise descriptor distance + descriptor loss + detector loss.  Replaces cdist,
+ * CircleLoss.forward / ContrastiveLoss.forward and DetLoss.forward (utils/loss.py:8-44, 111-141,
+ * 55-97, 149-158) as wired by trainer.py:90-98.
+ *
+ *   anchor, positive [P,D] f32; dist_keypts [P,P] f64 (keypts_is_f64=1) or f32;
+ *   anc_score, pos_score [P] f32 or NULL (then no detector loss);
+ *   dists [P,P] out (the `dists` the reference returns: for contrastive it carries the +10 bumps);
+ *   stats [8] out: [0] descriptor loss, [1] detector loss, [2] accuracy %, [3] mean furthest
+ *   positive, [4] mean average negative; furthest_pos [P], avg_neg [P] out.
+ *   aux: opaque buffer of d3f_pair_loss_aux_floats(P) floats, written by forward, read by backward.
+ */
+size_t d3f_pair_loss_aux_floats(int P);
+int d3f_pair_dist(const float* a, const float* b, int Pa, int Pb, int D, int metric, float* dists,
+                  d3f_stream stream);
+int d3f_pair_loss_forward(const float* anchor, const float* positive, int P, int D,
+                          const void* dist_keypts, int keypts_is_f64,
+                          const float* anc_score, const float* pos_score,
+                          int loss_kind, int metric, double safe_radius, float pos_margin,
+                          float neg_margin, float log_scale,
+                          float* dists, float* stats, float* furthest_pos, float* avg_neg,
+                          float* aux, d3f_stream stream);
+/* grad_losses [2] (device): dL/d(descriptor loss), dL/d(detector loss).
+ * outputs: grad_anchor, grad_positive [P,D]; grad_anc_score, grad_pos_score [P] or NULL. */
+int d3f_pair_loss_backward(const float* anchor, const float* positive, int P, int D,
+                           const void* dist_keypts, int keypts_is_f64,
+                           const float* anc_score, const float* pos_score,
+                           int loss_kind, int metric, double safe_radius, float pos_margin,
+                           float neg_margin, float log_scale,
+                           const float* dists, const float* aux, const float* grad_losses,
+                           float* grad_anchor, float* grad_positive,
+                           float* grad_anc_score, float* grad_pos_score, d3f_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* D3FEAT_B200_H */

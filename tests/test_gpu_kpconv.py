@@ -1,0 +1,83 @@
+"""GPU parity of the KPConv kernels: reference fixtures (fwd + bwd) and random shapes vs the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+import _inputs
+from conftest import golden
+from _util import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4  # BASELINE.json north_star: descriptors and loss within 1e-4 relative, fp32
+
+CASES = [
+    ("kpconv_rigid_2k", 2000, 64, 64, False, False, "linear", "sum", 100),
+    ("kpconv_rigid_c1", 1500, 1, 64, False, False, "linear", "sum", 101),
+    ("kpconv_gauss_closest", 600, 16, 24, False, False, "gaussian", "closest", 102),
+    ("kpconv_constant", 600, 16, 8, False, False, "constant", "sum", 103),
+    ("kpconv_deform", 800, 32, 32, True, False, "linear", "sum", 104),
+    ("kpconv_deform_mod", 800, 16, 32, True, True, "linear", "sum", 105),
+    ("kpconv_deform_gauss", 500, 16, 16, True, False, "gaussian", "sum", 106),
+]
+
+
+@pytest.mark.parametrize("name,n,cin,cout,deform,mod,infl,agg,seed", CASES)
+@pytest.mark.parametrize("idx_dtype", [torch.int64, torch.int32])
+def test_kpconv_module_vs_reference_fixture(cuda, name, n, cin, cout, deform, mod, infl, agg, seed, idx_dtype):
+    from d3feat.pytorch_b200.blocks import KPConv
+    g = golden(name)
+    case = _inputs.kpconv_case(n=n, cin=cin, cout=cout, seed=seed, deformable=deform, modulated=mod)
+    if cin == 1:
+        case["x"] = np.ones_like(case["x"])
+    m = KPConv(15, 3, cin, cout, case["extent"], case["radius"], KP_influence=infl, aggregation_mode=agg,
+               deformable=deform, modulated=mod).to(cuda)
+    m.load_state_dict(case["sd"], strict=True)
+    pts = torch.from_numpy(case["pts"]).to(cuda)
+    x = torch.from_numpy(case["x"]).to(cuda).requires_grad_(True)
+    inds = torch.from_numpy(g["inds"]).to(cuda).to(idx_dtype)
+    out = m(pts, pts, inds, x)
+    (out * torch.from_numpy(case["g"]).to(cuda)).sum().backward()
+    errs = {"out": rel_err(out.detach().cpu(), g["out"]), "dx": rel_err(x.grad.cpu(), g["dx"])}
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            errs["d_" + k] = rel_err(p.grad.cpu(), g["d_" + k.replace(".", "__")])
+    if deform:
+        errs["min_d2"] = rel_err(m.min_d2.cpu(), g["min_d2"])
+        errs["deformed_KP"] = rel_err(m.deformed_KP.detach().cpu(), g["deformed_KP"])
+    print(name, {k: "%.1e" % v for k, v in errs.items()})
+    assert max(errs.values()) < TOL, errs
+
+
+@pytest.mark.parametrize("nq,ns,H,cin,cout", [(1, 1, 1, 1, 1), (37, 50, 7, 3, 45), (300, 200, 40, 33, 64),
+                                              (129, 257, 19, 130, 17), (64, 64, 48, 256, 128), (5, 9, 0, 8, 8)])
+def test_kpconv_random_shapes_vs_oracle(cuda, nq, ns, H, cin, cout):
+    """Ragged shapes, shadow indices, strided index rows; CUDA vs the torch-CPU restatement."""
+    from oracle import model_ref
+    from d3feat.pytorch_b200.blocks import _KPConvFunction
+    rng = np.random.default_rng(nq * 1000 + H)
+    q = torch.from_numpy((rng.random((nq, 3)) * 0.2).astype(np.float32))
+    s = torch.from_numpy((rng.random((ns, 3)) * 0.2).astype(np.float32))
+    wide = torch.from_numpy(rng.integers(0, ns + 1, size=(nq, H + 3)).astype(np.int64))  # ns = shadow
+    inds = wide[:, :H]                                                                   # non-contiguous rows
+    x = torch.from_numpy(rng.standard_normal((ns, cin)).astype(np.float32)).requires_grad_(True)
+    W = torch.from_numpy((rng.standard_normal((15, cin, cout)) / np.sqrt(15 * cin)).astype(np.float32)).requires_grad_(True)
+    kp = torch.from_numpy((_inputs.unit_kernel_points() * 0.075).astype(np.float32))
+    gout = torch.from_numpy(rng.standard_normal((nq, cout)).astype(np.float32))
+    ref = model_ref.kpconv_rigid(q, s, inds, x, W, kp, 0.06)
+    (ref * gout).sum().backward()
+    xg = x.detach().to(cuda).requires_grad_(True)
+    Wg = W.detach().to(cuda).requires_grad_(True)
+    out, _ = _KPConvFunction.apply(q.to(cuda), s.to(cuda), wide.to(cuda)[:, :H], xg, Wg, kp.to(cuda), None, 0.06,
+                                   "linear", "sum", False, False)
+    (out * gout.to(cuda)).sum().backward()
+    scale = max(float(ref.abs().max()), 1e-6)
+    assert float((out.cpu() - ref.detach()).abs().max()) / scale < TOL
+    assert rel_err(xg.grad.cpu(), x.grad) < TOL if x.grad.abs().max() > 0 else float(xg.grad.abs().max()) == 0
+    assert rel_err(Wg.grad.cpu(), W.grad) < TOL if W.grad.abs().max() > 0 else float(Wg.grad.abs().max()) == 0
+
+
+def test_kpconv_rejects_cpu_tensors(built_lib):
+    from d3feat.pytorch_b200.blocks import KPConv
+    m = KPConv(15, 3, 4, 4, 0.06, 0.075)
+    with pytest.raises(RuntimeError, match="no CPU path|CUDA"):
+        m(torch.zeros(3, 3), torch.zeros(3, 3), torch.zeros(3, 2, dtype=torch.long), torch.zeros(3, 4))

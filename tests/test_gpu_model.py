@@ -1,0 +1,83 @@
+"""End-to-end GPU parity: device collate -> KPFCNN -> losses -> backward against the reference fixtures
+(oracle/make_golden.py ran the unmodified reference KPFCNN + CircleLoss + DetLoss on the same seeded pair)."""
+import numpy as np
+import pytest
+import torch
+
+import _inputs
+from conftest import golden
+from _util import rel_err
+from d3feat.pytorch_b200 import synthetic
+from d3feat.pytorch_b200.config import build_architecture, default_config
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.mark.parametrize("name,kw,limits", [
+    ("kpfcnn_rigid", {}, [40, 40, 40, 40, 40]),
+    ("kpfcnn_deform", dict(architecture=build_architecture(5, deformable_from=3)), [40, 40, 40, 120, 120]),
+])
+def test_kpfcnn_pair_vs_reference_fixture(cuda, name, kw, limits):
+    from d3feat.pytorch_b200.architectures import KPFCNN
+    from d3feat.pytorch_b200.dataloader import collate_fn_descriptor
+    from d3feat.pytorch_b200.loss import PairLoss
+    g = golden(name)
+    cfg = default_config(first_features_dim=32, **kw)
+    data = synthetic.fragment_pair(1500, seed=5, num_node=64)
+    batch = collate_fn_descriptor([data], cfg, limits)
+    # pyramid identical to the reference collate (shapes + index checksums)
+    assert [p.shape[0] for p in batch["points"]] == g["N"].tolist()
+    assert [p.shape[1] for p in batch["neighbors"]] == g["H"].tolist()
+    assert [int(x.sum()) for x in batch["neighbors"]] == g["nb_sum"].tolist()
+    assert [int(x.sum()) for x in batch["pools"]] == g["pool_sum"].tolist()
+    assert [int(x.sum()) for x in batch["upsamples"]] == g["up_sum"].tolist()
+    assert batch["neighbors"][0].dtype == torch.int64 and batch["stack_lengths"][0].dtype == torch.int32
+
+    model = KPFCNN(cfg).to(cuda)
+    model.load_state_dict(_inputs.kpfcnn_state_dict(cfg, seed=3), strict=True)
+    model.train()
+    feats, scores = model(batch)
+    c = batch["corr"].long()
+    n0 = int(batch["stack_lengths"][0][0])
+    o = PairLoss("circle", "euclidean", 10, 0.1, 0.1, 1.4)(feats[c[:, 0]], feats[c[:, 1] + n0], batch["dist_keypts"],
+                                                          scores[c[:, 0]], scores[c[:, 1] + n0])
+    (o["desc_loss"] + o["det_loss"]).backward()
+    gn = {k: float(p.grad.norm()) for k, p in model.named_parameters() if p.grad is not None}
+    errs = dict(features=rel_err(feats.detach().cpu(), g["features"]), scores=rel_err(scores.detach().cpu(), g["scores"]),
+                desc=rel_err(o["desc_loss"].detach().cpu(), g["desc_loss"]), det=rel_err(o["det_loss"].detach().cpu(), g["det_loss"]))
+    keys = [str(k) for k in g["grad_keys"]]
+    assert sorted(gn) == keys
+    errs["grad_norms"] = max(abs(gn[k] - float(v)) / max(float(v), 1e-12) for k, v in zip(keys, g["grad_norms"]))
+    print(name, {k: "%.1e" % v for k, v in errs.items()})
+    assert max(errs.values()) < TOL, errs
+    # eval-mode scores gate on exact equality: compare as a flip count
+    model.eval()
+    with torch.no_grad():
+        _, s_eval = model(batch)
+    flips = int(((s_eval.cpu().numpy() > 0) != (g["scores_eval"] > 0)).sum())
+    print("eval-mode local-max gate flips:", flips, "of", s_eval.shape[0])
+    assert flips <= max(3, s_eval.shape[0] // 200)
+
+
+def test_calibrate_neighbors_matches_percentile_rule(cuda, oracle_cpu):
+    from d3feat.pytorch_b200.dataloader import calibrate_neighbors, collate_fn_descriptor
+    cfg = default_config()
+
+    class DS:
+        config = cfg
+        def __len__(self): return 2
+        def __getitem__(self, i): return synthetic.fragment_pair(4000, seed=20 + i)
+    lim = calibrate_neighbors(DS(), cfg, collate_fn_descriptor, samples_threshold=10 ** 9)
+    assert lim.shape == (5,) and np.all(lim > 5) and np.all(lim < 200)
+    # level-0 limit = 80th percentile of the oracle's neighbour counts over the same two pairs
+    cnt = []
+    for i in range(2):
+        d = DS()[i]
+        p = np.concatenate([d[0], d[1]]); lens = np.array([4000, 4000], np.int32)
+        nb = oracle_cpu.batch_query(p, p, lens, lens, 0.075)
+        cnt.append((nb < 8000).sum(1))
+    cnt = np.concatenate(cnt)
+    hist = np.bincount(cnt, minlength=905)[:905]
+    cs = np.cumsum(hist)
+    assert int(lim[0]) == int((cs < 0.8 * cs[-1]).sum())
