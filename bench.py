@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- fragment-pairs/sec of the D3Feat hot path on B200 (BASELINE.json metric).
+
+One STEP = one 20k+20k synthetic fragment pair through the whole hot path (BASELINE config 3):
+device pyramid build (5 radius searches + 4 grid subsamplings + 4 pool + 4 upsample searches)
+-> KPFCNN forward (14 KPConv) -> circle + detector loss -> backward -> SGD step.
+
+  python bench.py --gpus N --steps K --warmup W        (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                  (the reference's CPU path, timed on host cores)
+
+Prints ONE JSON line (rank 0).  `value` = pairs/s with the raw pair already resident in HBM,
+`e2e` = the same through the public API from pinned HOST buffers with the loss read back.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+N_POINTS = 20000
+POOL = 4  # distinct synthetic pairs cycled through the steps (per rank)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--points", type=int, default=N_POINTS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fwd-only", action="store_true", help="diagnostic: forward + loss only")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------- helpers
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def kpconv_logical_bytes(nq, ns, H, cin, cout, K=15):
+    """algorithmic (logical gather) bytes of one KPConv forward."""
+    return nq * H * (4 * cin + 12 + 4) + nq * (12 + 4 * cout) + 4 * K * cin * cout
+
+
+def kpconv_flops(nq, H, cin, cout, K=15):
+    return 2 * K * nq * cin * (H + cout) + 12 * nq * H * K
+
+
+def make_pairs(n, count, seed0):
+    from d3feat.pytorch_b200 import synthetic
+    return [synthetic.fragment_pair(n, seed=seed0 + i) for i in range(count)]
+
+
+# ------------------------------------------------------------------------------------------- reference arm
+def cpu_reference_setup(n_points):
+    import _inputs
+    from d3feat.pytorch_b200.config import default_config
+    from oracle import cpu
+    cfg = default_config()
+    sd = _inputs.kpfcnn_state_dict(cfg, seed=0)
+    impl = "ref" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libd3feat_ref.so")) else "port"
+    cpu.build()
+    return cfg, sd, impl
+
+
+def cpu_limits(pairs, cfg, impl):
+    """neighborhood_limits by the reference rule (dataloader.py:191-223) from the CPU oracle."""
+    from oracle import pipeline
+    hist_n = int(np.ceil(4 / 3 * np.pi * (cfg.deform_radius + 1) ** 3))
+    hists = np.zeros((cfg.num_layers, hist_n), np.int64)
+    for d in pairs:
+        b = pipeline.cpu_collate(d, cfg, [hist_n] * cfg.num_layers, impl=impl)
+        for l, m in enumerate(b["neighbors"]):
+            c = (m < m.shape[0]).sum(1).numpy()
+            hists[l] += np.bincount(c, minlength=hist_n)[:hist_n]
+    cs = np.cumsum(hists.T, axis=0)
+    return (cs < 0.8 * cs[hist_n - 1]).sum(0).tolist()
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path on this box's host cores: reference C++
+    (oracle/_ref) for the pyramid + the torch-CPU restatement of KPFCNN / losses (the reference's
+    Python cannot travel to the GPU box).  Under torchrun only rank 0 works."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pipeline
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg, sd, impl = cpu_reference_setup(args.points)
+    pairs = make_pairs(args.points, min(POOL, max(1, args.steps)), 0)
+    limits = LIMITS_20K if args.points == N_POINTS else cpu_limits(pairs[:1], cfg, impl)
+    sgd = {}
+    for i in range(args.warmup):
+        pipeline.cpu_pair_step(pairs[i % len(pairs)], sd, cfg, limits, impl=impl, backward=not args.fwd_only, sgd=sgd)
+    t0 = time.perf_counter()
+    stages = {}
+    for i in range(args.steps):
+        t, _ = pipeline.cpu_pair_step(pairs[i % len(pairs)], sd, cfg, limits, impl=impl, backward=not args.fwd_only, sgd=sgd)
+        for k, v in t.items():
+            stages[k] = stages.get(k, 0.0) + v
+    dt = time.perf_counter() - t0
+    val = args.steps / dt
+    sample = "%d pairs of %d+%d points, whole path (collate+fwd+loss+bwd), %s" % (
+        args.steps, args.points, args.points, "pyramid by the reference C++ (oracle/_ref), model by the torch-CPU oracle"
+        if impl == "ref" else "oracle port")
+    line = {"impl": "reference", "metric": "fragment-pairs/sec", "value": val, "unit": "pairs/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, limits),
+            "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "reference" if impl == "ref" else "port",
+                             "sample": sample, "stage_seconds_per_pair": {k: v / args.steps for k, v in stages.items()}},
+            "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+LIMITS_20K = [35, 42, 42, 45, 47]  # 80th-percentile rule on the synthetic 20k pairs (recomputed on the device below)
+
+
+def workload_config(args, limits):
+    return {"workload": "BASELINE config 3: %d+%d-point synthetic room-shell pair, device pyramid build + KPFCNN fwd "
+                        "(default arch, 24.3M params, K=15, first_features_dim=128) + circle & detector loss (P=128) "
+                        "+ bwd + SGD step" % (args.points, args.points),
+            "points_per_fragment": args.points, "neighborhood_limits": [int(v) for v in limits], "pairs_per_step_per_gpu": 1,
+            "parallelism": "dp%d (1 pair per GPU, descriptor all-gather)" % args.gpus,
+            "l2_policy": "256 MiB L2 flush write between timed steps (outside the per-step event brackets)"}
+
+
+# ------------------------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch.distributed as dist
+    from d3feat.pytorch_b200 import _lib, ops
+    from d3feat.pytorch_b200.architectures import KPFCNN
+    from d3feat.pytorch_b200.config import default_config
+    from d3feat.pytorch_b200.dataloader import calibrate_neighbors, collate_fn_descriptor
+    from d3feat.pytorch_b200.loss import PairLoss
+    from d3feat.pytorch_b200 import parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()  # raises if the sm_100a library has not been built: no fallback
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+    cfg = default_config()
+    torch.manual_seed(0); np.random.seed(0)
+    model = KPFCNN(cfg).to(dev)
+    model.train()
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.98, weight_decay=1e-6)  # config.py:62-69
+    loss_fn = PairLoss("circle", "euclidean", cfg.log_scale, cfg.safe_radius, cfg.pos_margin, cfg.neg_margin)
+
+    pairs = make_pairs(args.points, POOL, 100 * rank)
+
+    class _DS:
+        config = cfg
+        def __len__(self): return 2
+        def __getitem__(self, i): return pairs[i]
+    limits = [int(v) for v in calibrate_neighbors(_DS(), cfg, collate_fn_descriptor, samples_threshold=10 ** 9)]
+
+    host = [tuple(torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in p) for p in pairs]
+    devp = [tuple(t.to(dev) for t in p) for p in host]
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(data, read_loss):
+        batch = collate_fn_descriptor([data], cfg, limits)
+        feats, scores = model(batch)
+        c = batch["corr"].long()
+        n0 = data[0].shape[0]
+        a, p = feats[c[:, 0]], feats[c[:, 1] + n0]
+        sa, sp = scores[c[:, 0]], scores[c[:, 1] + n0]
+        if world > 1:
+            out = parallel.cross_fragment_loss(loss_fn, a, p, batch["dist_keypts"], sa, sp)
+        else:
+            out = loss_fn(a, p, batch["dist_keypts"], sa, sp)
+        loss = out["desc_loss"] * cfg.desc_loss_weight + out["det_loss"] * cfg.det_loss_weight
+        if not args.fwd_only:
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            if world > 1:
+                parallel.allreduce_gradients(model)
+            opt.step()
+        return float(loss) if read_loss else loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(kind, steps, profile=False):
+        src = devp if kind == "device" else host
+        evs = []
+        barrier()
+        ops.PROFILE = {} if profile else None
+        launches0 = lib.d3f_launch_count()
+        wall0 = time.perf_counter()
+        for i in range(steps):
+            flush.fill_(i & 0xFF)          # L2 flush, outside the event bracket
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step(src[i % POOL], read_loss=(kind == "host"))
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        wall = time.perf_counter() - wall0
+        prof, ops.PROFILE = ops.PROFILE, None
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), wall, lib.d3f_launch_count() - launches0, prof
+
+    for i in range(max(args.warmup, 3)):
+        step(devp[i % POOL], False)
+    for i in range(2):
+        step(host[i % POOL], True)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, wall_dev, launches, prof = timed("device", args.steps, profile=True)
+    ms_e2e, wall_e2e, _, _ = timed("host", args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk, pk_src = peaks()
+    # roofline of the dominant op: the KPConv forward with the most algorithmic bytes (L0 resnetb 32->32)
+    fwd = {k: v for k, v in prof.items() if k[0] == "kpconv_fwd"}
+    per_layer, tot_bytes, tot_ms = [], 0, 0.0
+    for k, evs in fwd.items():
+        _, nq, ns, H, cin, cout, deformed = k
+        calls_per_step = len(evs) / args.steps
+        avg_ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+        by = kpconv_logical_bytes(nq, ns, H, cin, cout)
+        per_layer.append({"nq": nq, "ns": ns, "H": H, "cin": cin, "cout": cout, "calls_per_step": calls_per_step,
+                          "ms": avg_ms, "logical_MB": by / 1e6, "GBps": by / avg_ms / 1e6,
+                          "TFLOPs": kpconv_flops(nq, H, cin, cout) / avg_ms / 1e9})
+        tot_bytes += by * calls_per_step
+        tot_ms += avg_ms * calls_per_step
+    per_layer.sort(key=lambda d: -d["logical_MB"])
+    dom = per_layer[0]
+    stage_ms = {}
+    for k, evs in prof.items():
+        stage_ms[k[0]] = stage_ms.get(k[0], 0.0) + sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    roofline = {"bound": "hbm", "achieved": dom["GBps"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": dom["GBps"] / pk["hbm_gbs"], "traffic": None,
+                "kernel": "KPConv forward op (kp_rowpos + kp_correlate + kp_gemm) of the layer with the most algorithmic "
+                          "bytes: Nq=%d Ns=%d H=%d Cin=%d Cout=%d" % (dom["nq"], dom["ns"], dom["H"], dom["cin"], dom["cout"]),
+                "algorithmic_bytes_per_launch": dom["logical_MB"] * 1e6, "avg_ms_per_launch": dom["ms"],
+                "peak_source": pk_src + ", burst copy bandwidth",
+                "all_kpconv_fwd": {"logical_GB_per_step": tot_bytes / 1e9, "ms_per_step": tot_ms,
+                                   "GBps": tot_bytes / tot_ms / 1e6, "frac": tot_bytes / tot_ms / 1e6 / pk["hbm_gbs"]},
+                "layers": per_layer[:6], "stage_ms_per_step": stage_ms}
+
+    pairs_per_step = world
+    value = pairs_per_step * args.steps / (ms_dev / 1e3)
+    e2e_val = pairs_per_step * args.steps / (ms_e2e / 1e3)
+    line = {"metric": "fragment-pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, limits),
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4 + 17 * 8,
+                    "api": "collate_fn_descriptor(pinned host tensors) -> KPFCNN -> PairLoss -> backward -> SGD -> float(loss)"},
+            "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
+            "wall_s": {"device": wall_dev, "e2e": wall_e2e},
+            "roofline": roofline}
+
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import pipeline
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        cfg_c, sd, impl = cpu_reference_setup(args.points)
+        sgd = {}
+        pipeline.cpu_pair_step(pairs[0], sd, cfg_c, limits, impl=impl, backward=not args.fwd_only, sgd=sgd)
+        t0 = time.perf_counter()
+        n_cpu, stages = 0, {}
+        while n_cpu < 3 or (time.perf_counter() - t0 < 10 and n_cpu < 10):
+            t, _ = pipeline.cpu_pair_step(pairs[n_cpu % POOL], sd, cfg_c, limits, impl=impl, backward=not args.fwd_only, sgd=sgd)
+            for k, v in t.items():
+                stages[k] = stages.get(k, 0.0) + v
+            n_cpu += 1
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": n_cpu / dt, "unit": "pairs/s", "cores": cores,
+                                "kind": "reference" if impl == "ref" else "port",
+                                "sample": "%d pairs of the same workload (pyramid: reference C++ via oracle/_ref, single thread as "
+                                          "in the reference; model+loss+bwd: torch-CPU oracle on %d threads)" % (n_cpu, cores),
+                                "stage_seconds_per_pair": {k: v / n_cpu for k, v in stages.items()}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -24,6 +24,7 @@ c_p, c_i, c_f, c_d, c_sz, c_i64 = (ctypes.c_void_p, ctypes.c_int, ctypes.c_float
 SIGNATURES = {
     "d3f_version": (c_i, []),
     "d3f_last_error_string": (ctypes.c_char_p, []),
+    "d3f_launch_count": (ctypes.c_ulonglong, []),
     "d3f_radius_neighbors_workspace_bytes": (c_sz, [c_i, c_i, c_i]),
     "d3f_radius_neighbors": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_i, c_p, c_i, c_p, c_i, c_p, c_sz, c_p]),
     "d3f_grid_subsample_workspace_bytes": (c_sz, [c_i, c_i]),

@@ -17,7 +17,12 @@ void d3f_set_error(const char* fmt, ...);
         }                                                                                      \
     } while (0)
 
-#define D3F_CHECK_LAUNCH() D3F_CHECK_CUDA(cudaGetLastError())
+extern unsigned long long g_d3f_launches;   // kernels launched by this library (diagnostic; not thread-safe)
+#define D3F_CHECK_LAUNCH()                                                                     \
+    do {                                                                                       \
+        ++g_d3f_launches;                                                                      \
+        D3F_CHECK_CUDA(cudaGetLastError());                                                    \
+    } while (0)
 
 #define D3F_REQUIRE(cond, code, msg)                                                           \
     do {                                                                                       \

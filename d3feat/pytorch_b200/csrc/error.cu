@@ -12,3 +12,6 @@ void d3f_set_error(const char* fmt, ...) {
 
 extern "C" int d3f_version(void) { return 100; }
 extern "C" const char* d3f_last_error_string(void) { return g_err; }
+
+unsigned long long g_d3f_launches = 0;
+extern "C" unsigned long long d3f_launch_count(void) { return g_d3f_launches; }

@@ -13,7 +13,31 @@ AGGREGATION = {"sum": 0, "closest": 1}
 METRIC = {"euclidean": 0, "sqeuclidean": 1, "cityblock": 2, "cosine": 3, "arccosine": 4}
 LOSS_KIND = {"circle": 0, "contrastive": 1}
 
-launch_count = 0  # number of C-ABI hot-path calls issued (bench.py reports kernel launches from ncu)
+launch_count = 0  # number of C-ABI hot-path calls issued
+
+# Optional per-op CUDA-event timing (bench.py switches it on for its timed region): a dict
+# tag -> [(start_event, end_event), ...] recorded on the stream the kernels are launched on.
+PROFILE = None
+
+
+class _Timed:
+    __slots__ = ("tag", "ev")
+
+    def __init__(self, tag):
+        self.tag = tag
+        self.ev = None
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.ev[0].record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ev is not None:
+            self.ev[1].record()
+            PROFILE.setdefault(self.tag, []).append(self.ev)
+        return False
 
 
 def _p(t):
@@ -63,7 +87,8 @@ def radius_neighbors_raw(queries, supports, q_len, s_len, radius, max_cols, inde
     ws = _ws(ws_bytes, dev)
     global launch_count
     launch_count += 1
-    _lib.check(lib.d3f_radius_neighbors(_p(queries), _p(supports), _p(q_len), _p(s_len), nb, nq, ns,
+    with _Timed(("radius_neighbors", nq, ns)):
+      _lib.check(lib.d3f_radius_neighbors(_p(queries), _p(supports), _p(q_len), _p(s_len), nb, nq, ns,
                                         float(radius), int(max_cols) if not count_only else 0, _p(out),
                                         1 if index_dtype == torch.int64 else 0, _p(info), int(row_capacity),
                                         _p(ws), ws.numel(), _stream()))
@@ -105,7 +130,8 @@ def grid_subsample(points, lengths, sample_dl):
     ws = _ws(lib.d3f_grid_subsample_workspace_bytes(n, nb), dev)
     global launch_count
     launch_count += 1
-    _lib.check(lib.d3f_grid_subsample(_p(points), _p(lengths), nb, n, float(sample_dl), _p(out), _p(out_len),
+    with _Timed(("grid_subsample", n)):
+      _lib.check(lib.d3f_grid_subsample(_p(points), _p(lengths), nb, n, float(sample_dl), _p(out), _p(out_len),
                                       _p(ws), ws.numel(), _stream()))
     host_len = out_len.tolist()
     if any(v < 0 for v in host_len):
@@ -140,7 +166,8 @@ def kpconv_forward(q_pts, s_pts, inds, x, weights, kernel_points, extent, influe
     ws = _ws(lib.d3f_kpconv_workspace_bytes(nq, ns, H, K, cin, cout), dev)
     global launch_count
     launch_count += 1
-    _lib.check(lib.d3f_kpconv_forward(_p(q_pts), _p(s_pts), _p(inds), 1 if inds.dtype == torch.int64 else 0,
+    with _Timed(("kpconv_fwd", nq, ns, H, cin, cout, bool(deformed))):
+      _lib.check(lib.d3f_kpconv_forward(_p(q_pts), _p(s_pts), _p(inds), 1 if inds.dtype == torch.int64 else 0,
                                       inds.stride(0) if H > 0 else 0, _p(x), _p(weights), _p(kernel_points),
                                       1 if deformed else 0, _p(modulations), nq, ns, H, K, cin, cout,
                                       float(extent), INFLUENCE[influence], AGGREGATION[aggregation],
@@ -162,7 +189,8 @@ def kpconv_backward(q_pts, s_pts, inds, x, weights, kernel_points, extent, influ
     ws = _ws(lib.d3f_kpconv_workspace_bytes(nq, ns, H, K, cin, cout), dev)
     global launch_count
     launch_count += 1
-    _lib.check(lib.d3f_kpconv_backward(_p(q_pts), _p(s_pts), _p(inds), 1 if inds.dtype == torch.int64 else 0,
+    with _Timed(("kpconv_bwd", nq, ns, H, cin, cout, bool(deformed))):
+      _lib.check(lib.d3f_kpconv_backward(_p(q_pts), _p(s_pts), _p(inds), 1 if inds.dtype == torch.int64 else 0,
                                        inds.stride(0) if H > 0 else 0, _p(x), _p(weights), _p(kernel_points),
                                        1 if deformed else 0, _p(modulations), nq, ns, H, K, cin, cout,
                                        float(extent), INFLUENCE[influence], AGGREGATION[aggregation],

@@ -44,6 +44,8 @@ enum { D3F_LOSS_CIRCLE = 0, D3F_LOSS_CONTRASTIVE = 1 };                         
 
 int d3f_version(void);
 const char* d3f_last_error_string(void);
+/* number of CUDA kernels this library has launched in this process (diagnostic counter) */
+unsigned long long d3f_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Radius neighbours.  Replaces radius_neighbors.batch_query

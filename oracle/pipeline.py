@@ -59,9 +59,10 @@ def cpu_collate(data, config, limits, impl="port"):
     return out
 
 
-def cpu_pair_step(data, sd, config, limits, impl="ref", backward=True):
-    """One whole pair on the CPU: collate -> forward -> circle + detector loss (-> backward).
-    Returns (seconds per stage dict, loss value)."""
+def cpu_pair_step(data, sd, config, limits, impl="ref", backward=True, sgd=None):
+    """One whole pair on the CPU: collate -> forward -> circle + detector loss (-> backward -> SGD step,
+    training_3DMatch.py:62-69: lr 0.01, momentum 0.98, weight decay 1e-6; `sgd` = dict of momentum buffers,
+    updated in place together with `sd`).  Returns (seconds per stage dict, loss value)."""
     t = {}
     t0 = time.perf_counter()
     batch = cpu_collate(data, config, limits, impl=impl)
@@ -79,4 +80,16 @@ def cpu_pair_step(data, sd, config, limits, impl="ref", backward=True):
             t0 = time.perf_counter()
             loss.backward()
             t["backward"] = time.perf_counter() - t0
-    return t, float(loss)
+            if sgd is not None:
+                t0 = time.perf_counter()
+                with torch.no_grad():
+                    for k, prm in params.items():
+                        if prm.grad is None:
+                            continue
+                        g = prm.grad + 1e-6 * prm
+                        buf = sgd.get(k)
+                        buf = g.clone() if buf is None else buf.mul_(0.98).add_(g)
+                        sgd[k] = buf
+                        sd[k] = (prm - 0.01 * buf).detach()
+                t["sgd"] = time.perf_counter() - t0
+    return t, float(loss.detach())

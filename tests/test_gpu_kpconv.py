@@ -70,7 +70,7 @@ def test_kpconv_random_shapes_vs_oracle(cuda, nq, ns, H, cin, cout):
     out, _ = _KPConvFunction.apply(q.to(cuda), s.to(cuda), wide.to(cuda)[:, :H], xg, Wg, kp.to(cuda), None, 0.06,
                                    "linear", "sum", False, False)
     (out * gout.to(cuda)).sum().backward()
-    scale = max(float(ref.abs().max()), 1e-6)
+    scale = max(float(ref.detach().abs().max()), 1e-6)
     assert float((out.cpu() - ref.detach()).abs().max()) / scale < TOL
     assert rel_err(xg.grad.cpu(), x.grad) < TOL if x.grad.abs().max() > 0 else float(xg.grad.abs().max()) == 0
     assert rel_err(Wg.grad.cpu(), W.grad) < TOL if W.grad.abs().max() > 0 else float(Wg.grad.abs().max()) == 0
