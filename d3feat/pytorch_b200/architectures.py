@@ -7,6 +7,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import ops
 from .blocks import block_decider
 
 _LAYER_CHANGE = ('pool', 'strided', 'upsample', 'global')
@@ -69,19 +70,7 @@ class KPFCNN(nn.Module):
         return F.normalize(x, p=2, dim=-1), scores
 
     def detection_scores(self, inputs, features):
-        """Saliency x channel-max keypoint score (architectures.py:322-368); stock PyTorch
-        (next in line for a fused kernel)."""
-        neighbor = inputs['neighbors'][0].long()
-        n = features.shape[0]
-        feats = torch.cat([features, torch.zeros_like(features[:1])], dim=0)
-        neighbor = torch.cat([neighbor, torch.full_like(neighbor[:1], n)], dim=0)
-        feats = feats / (feats.max() + 1e-6)
-        nf = feats[neighbor]                                            # [N+1, H, C]
-        count = (nf.sum(dim=-1) != 0).sum(dim=-1, keepdim=True).clamp(min=1)
-        local_max_score = F.softplus(feats - nf.sum(dim=1) / count)
-        depth_wise_max_score = feats / (1e-6 + feats.max(dim=1, keepdim=True)[0])
-        scores = (local_max_score * depth_wise_max_score).max(dim=1, keepdim=True)[0]
-        if not self.training:  # hard local-max gate at test time
-            is_local_max = feats == nf.max(dim=1)[0]
-            scores = scores * is_local_max.float().max(dim=1, keepdim=True)[0]
-        return scores[:-1]
+        """Saliency x channel-max keypoint score (architectures.py:322-368): neighbour-mean saliency
+        softplus(f - mean_nb f), depth-wise ratio f / max_c f, max over channels, and at test time the
+        exact-equality local-max gate.  One fused warp-per-point kernel (d3f_detection_scores_*)."""
+        return ops.detection_scores(features, inputs['neighbors'][0], not self.training)

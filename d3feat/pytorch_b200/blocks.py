@@ -19,21 +19,21 @@ from .kernel_points import load_kernels
 # ----------------------------------------------------------------------------- small tensor helpers
 def gather(x, idx, method=2):
     """x[idx] (reference blocks.py:35-66 offers three equivalent formulations; one is enough here)."""
+    if idx.dim() == 1 and x.dim() == 2 and x.is_cuda:
+        return ops.gather_rows(x, idx)
     return x[idx.long()]
 
 
-def _with_shadow_row(x):
-    return torch.cat([x, x.new_zeros((1,) + tuple(x.shape[1:]))], dim=0)
-
-
 def closest_pool(x, inds):
-    """Feature of the closest (first-column) neighbour; shadow -> zeros (blocks.py:79-91)."""
-    return _with_shadow_row(x)[inds[:, 0].long()]
+    """Feature of the closest (first-column) neighbour; shadow -> zeros (blocks.py:79-91).
+    One row-gather kernel; the backward is an atomic row scatter instead of ATen's sort-based index_put."""
+    return ops.gather_rows(x, inds[:, 0])
 
 
 def max_pool(x, inds):
-    """Channel-wise max over each pooling neighbourhood; the shadow row is zero (blocks.py:94-110)."""
-    return _with_shadow_row(x)[inds.long()].max(dim=1)[0]
+    """Channel-wise max over each pooling neighbourhood; the shadow row is zero (blocks.py:94-110).
+    One warp-per-query kernel that keeps the arg-max rows for the backward scatter."""
+    return ops.max_pool(x, inds)
 
 
 def global_average(x, batch_lengths):

@@ -1,0 +1,320 @@
+// Neighbourhood pooling / row gather / detection score kernels: the gathers that sit between the
+// KPConv layers.  The reference issues them as ATen advanced indexing
+// (models/blocks.py:79-110, models/architectures.py:322-368) whose backward (sort-based index_put)
+// dominates a training step on the GPU; here every op is one warp-per-row kernel, forward and backward.
+//
+//   max_pool      out[i,c] = max_h xpad[inds[i,h], c]     (shadow row = 0, blocks.py:94-110)
+//   gather_rows   out[m,:] = xpad[idx[m], :]               (closest_pool blocks.py:79-91, row selects)
+//   det_scores    D3Feat keypoint score (architectures.py:322-368), train and eval mode
+#include "common.cuh"
+
+namespace {
+
+template <bool IDX64>
+__device__ __forceinline__ long long load_idx(const void* p, size_t off) {
+    return IDX64 ? ((const long long*)p)[off] : (long long)((const int*)p)[off];
+}
+
+// ------------------------------------------------------------------------------------------- max pool
+template <bool IDX64>
+__global__ void mp_forward_kernel(const float* __restrict__ x, const void* __restrict__ inds, long long ld, int nq,
+                                  int ns, int H, int C, float* __restrict__ out, int* __restrict__ arg) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= nq) return;
+    for (int c0 = 0; c0 < C; c0 += 128) {
+        const int c = c0 + lane * 4;
+        float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        int who[4] = {-1, -1, -1, -1};
+        for (int h = 0; h < H; ++h) {
+            const long long idx = load_idx<IDX64>(inds, (size_t)warp * ld + h);
+            const bool real = idx >= 0 && idx < ns;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (real && c < C) {
+                if (c + 3 < C && (C & 3) == 0) {
+                    const float4 t = *(const float4*)&x[(size_t)idx * C + c];
+                    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                } else {
+                    for (int e = 0; e < 4; ++e) if (c + e < C) v[e] = x[(size_t)idx * C + c + e];
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (v[e] > best[e]) { best[e] = v[e]; who[e] = real ? (int)idx : -1; }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (c + e < C) {
+                out[(size_t)warp * C + c + e] = H > 0 ? best[e] : 0.f;
+                arg[(size_t)warp * C + c + e] = who[e];
+            }
+    }
+}
+
+__global__ void mp_backward_kernel(const float* __restrict__ g, const int* __restrict__ arg, size_t total, int C,
+                                   float* __restrict__ gx) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int a = arg[t];
+    if (a >= 0) atomicAdd(&gx[(size_t)a * C + (t % C)], g[t]);
+}
+
+// ------------------------------------------------------------------------------------------- row gather
+template <bool IDX64>
+__global__ void gr_forward_kernel(const float* __restrict__ x, const void* __restrict__ idx, long long stride, int m,
+                                  int ns, int C, float* __restrict__ out) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= m) return;
+    const long long i = load_idx<IDX64>(idx, (size_t)warp * stride);
+    const bool real = i >= 0 && i < ns;
+    for (int c = lane; c < C; c += 32) out[(size_t)warp * C + c] = real ? x[(size_t)i * C + c] : 0.f;
+}
+
+template <bool IDX64>
+__global__ void gr_backward_kernel(const float* __restrict__ g, const void* __restrict__ idx, long long stride, int m,
+                                   int ns, int C, float* __restrict__ gx) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= m) return;
+    const long long i = load_idx<IDX64>(idx, (size_t)warp * stride);
+    if (i < 0 || i >= ns) return;
+    for (int c = lane; c < C; c += 32) atomicAdd(&gx[(size_t)i * C + c], g[(size_t)warp * C + c]);
+}
+
+// ------------------------------------------------------------------------------------------- detection scores
+// global max over F and the zero shadow row; also its flat argmax (first occurrence) for the backward
+__global__ void ds_gmax_kernel(const float* __restrict__ F, size_t total, unsigned long long* __restrict__ packed) {
+    // packed = (ordered float bits << 32) | (0xFFFFFFFF - index): atomicMax gives max value, then smallest index
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long best = 0;
+    for (; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const float v = F[t];
+        unsigned int b = __float_as_uint(v);
+        b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+        const unsigned long long k = ((unsigned long long)b << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)t);
+        best = k > best ? k : best;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+        best = ob > best ? ob : best;
+    }
+    if ((threadIdx.x & 31) == 0) atomicMax(packed, best);
+}
+
+__device__ __forceinline__ float ds_unpack_max(unsigned long long packed, long long* arg) {
+    unsigned int b = (unsigned int)(packed >> 32);
+    b = (b & 0x80000000u) ? (b & 0x7FFFFFFFu) : ~b;
+    float g = __uint_as_float(b);
+    *arg = (long long)(0xFFFFFFFFu - (unsigned int)(packed & 0xFFFFFFFFu));
+    if (!(g > 0.0f)) { g = 0.0f; *arg = -1; }  // the appended zero shadow row wins (architectures.py:330-331)
+    return g;
+}
+
+__device__ __forceinline__ float ds_softplus(float v) { return v > 20.0f ? v : log1pf(expf(v)); }
+__device__ __forceinline__ float ds_sigmoid(float v) { return v > 20.0f ? 1.0f : 1.0f / (1.0f + expf(-v)); }
+
+// One warp per point; lane = channel (C <= 32).  Forward writes score[i]; backward (gscore != null) writes
+// the direct part of dL/dF and accumulates dL/dgmax.
+template <bool IDX64, bool BACKWARD>
+__global__ void ds_kernel(const float* __restrict__ F, const void* __restrict__ nb, long long ld, int n, int H, int C,
+                          const unsigned long long* __restrict__ packed, int eval_mode, float* __restrict__ score,
+                          const float* __restrict__ gscore, float* __restrict__ gF, float* __restrict__ gacc) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= n) return;
+    long long garg;
+    const float inv = 1.0f / (ds_unpack_max(*packed, &garg) + 1e-6f);
+    float gs = 0.f;
+    if (BACKWARD) {
+        gs = gscore[i];
+        if (gs == 0.0f) return;  // only the selected correspondences carry gradient
+    }
+    const bool act = lane < C;
+    const float f = act ? F[(size_t)i * C + lane] * inv : 0.f;
+    float sum = 0.f, nmax = -INFINITY;
+    int cnt = 0;
+    for (int h = 0; h < H; ++h) {
+        const long long j = load_idx<IDX64>(nb, (size_t)i * ld + h);
+        const bool real = j >= 0 && j < n;
+        const float v = (real && act) ? F[(size_t)j * C + lane] * inv : 0.f;
+        float rs = v;
+        for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+        cnt += rs != 0.0f;
+        sum += v;
+        nmax = fmaxf(nmax, v);
+    }
+    const float cn = (float)max(cnt, 1);
+    const float mean = sum / cn;
+    const float local = ds_softplus(f - mean);
+    float rmax = act ? f : -INFINITY;
+    for (int o = 16; o > 0; o >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+    const float den = 1e-6f + rmax;
+    const float depth = f / den;
+    float s = act ? local * depth : -INFINITY;
+    // max over channels with first-index argmax
+    float best = s; int bc = lane;
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+        if (ob > best || (ob == best && oc < bc)) { best = ob; bc = oc; }
+    }
+    float gate = 1.0f;
+    if (eval_mode) {
+        const unsigned any = __ballot_sync(0xffffffffu, act && H > 0 && f == nmax);
+        gate = any ? 1.0f : 0.0f;
+    }
+    if (!BACKWARD) {
+        if (lane == 0) score[i] = best * gate;
+        return;
+    }
+    // ---- backward: score = local[c*] * depth[c*] (* gate, constant)
+    const float g = gs * gate;
+    // values at the winning channel, broadcast
+    const float local_s = __shfl_sync(0xffffffffu, local, bc);
+    const float depth_s = __shfl_sync(0xffffffffu, depth, bc);
+    const float f_s = __shfl_sync(0xffffffffu, f, bc);
+    const float mean_s = __shfl_sync(0xffffffffu, mean, bc);
+    const float dlocal = g * depth_s;                 // dL/dlocal[c*]
+    const float ddepth = g * local_s;                 // dL/ddepth[c*]
+    const float sg = ds_sigmoid(f_s - mean_s);
+    // d f[c*] : local via softplus, depth numerator;  d rmax : depth denominator;  d mean[c*]
+    const float df_cs = dlocal * sg + ddepth / den;
+    const float drmax = -ddepth * f_s / (den * den);
+    const float dmean = -dlocal * sg;
+    // row argmax of f (first index) receives drmax
+    float rbest = act ? f : -INFINITY; int rc = lane;
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, rbest, o);
+        const int oc = __shfl_xor_sync(0xffffffffu, rc, o);
+        if (ob > rbest || (ob == rbest && oc < rc)) { rbest = ob; rc = oc; }
+    }
+    // dL/df for this row (normalised features); convert to dL/dF = df * inv and accumulate sum(df * f) for gmax
+    float df_own = 0.f;
+    if (lane == bc) df_own += df_cs;
+    if (lane == rc) df_own += drmax;
+    float acc = df_own * f;
+    if (act && df_own != 0.0f) atomicAdd(&gF[(size_t)i * C + lane], df_own * inv);
+    // neighbours: mean[c*] = sum_h nf[h, c*] / cn  -> each real neighbour gets dmean / cn at channel c*
+    const float dn = dmean / cn;
+    if (dn != 0.0f) {
+        for (int h0 = 0; h0 < H; h0 += 32) {
+            const int h = h0 + lane;
+            if (h < H) {
+                const long long j = load_idx<IDX64>(nb, (size_t)i * ld + h);
+                if (j >= 0 && j < n) {
+                    atomicAdd(&gF[(size_t)j * C + bc], dn * inv);
+                    acc += dn * (F[(size_t)j * C + bc] * inv);
+                }
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    // f = F / (gmax + eps): dL/dgmax = -sum(df * f) / (gmax + eps)
+    if (lane == 0 && acc != 0.0f) atomicAdd(gacc, -acc * inv);
+}
+
+__global__ void ds_gmax_backward_kernel(const unsigned long long* __restrict__ packed, const float* __restrict__ gacc,
+                                        float* __restrict__ gF) {
+    long long garg;
+    ds_unpack_max(*packed, &garg);
+    if (garg >= 0) gF[garg] += *gacc;
+}
+
+}  // namespace
+
+extern "C" int d3f_max_pool_forward(const float* x, const void* inds, int idx_is_64, int64_t ld_inds, int n_queries,
+                                    int n_supports, int n_neighbors, int channels, float* out, int32_t* argmax,
+                                    d3f_stream stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    D3F_REQUIRE(n_queries >= 0 && n_supports >= 0 && n_neighbors >= 0 && channels >= 1, D3F_ERR_INVALID, "bad sizes");
+    if (n_queries == 0) return D3F_OK;
+    D3F_REQUIRE(x && (inds || n_neighbors == 0) && out && argmax, D3F_ERR_INVALID, "null pointer");
+    auto kern = idx_is_64 ? mp_forward_kernel<true> : mp_forward_kernel<false>;
+    kern<<<d3f_ceil_div(n_queries, 8), 256, 0, stream>>>(x, inds, (long long)ld_inds, n_queries, n_supports, n_neighbors,
+                                                        channels, out, argmax);
+    D3F_CHECK_LAUNCH();
+    return D3F_OK;
+}
+
+extern "C" int d3f_max_pool_backward(const float* grad_out, const int32_t* argmax, int n_queries, int n_supports,
+                                     int channels, float* grad_x, d3f_stream stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    D3F_REQUIRE(n_queries >= 0 && n_supports >= 0 && channels >= 1, D3F_ERR_INVALID, "bad sizes");
+    D3F_REQUIRE(grad_x || n_supports == 0, D3F_ERR_INVALID, "null pointer");
+    if (n_supports > 0) D3F_CHECK_CUDA(cudaMemsetAsync(grad_x, 0, sizeof(float) * (size_t)n_supports * channels, stream));
+    if (n_queries == 0 || n_supports == 0) return D3F_OK;
+    D3F_REQUIRE(grad_out && argmax, D3F_ERR_INVALID, "null pointer");
+    const size_t total = (size_t)n_queries * channels;
+    mp_backward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(grad_out, argmax, total, channels, grad_x);
+    D3F_CHECK_LAUNCH();
+    return D3F_OK;
+}
+
+extern "C" int d3f_gather_rows_forward(const float* x, const void* idx, int idx_is_64, int64_t idx_stride, int n_rows,
+                                       int n_supports, int channels, float* out, d3f_stream stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    D3F_REQUIRE(n_rows >= 0 && n_supports >= 0 && channels >= 1, D3F_ERR_INVALID, "bad sizes");
+    if (n_rows == 0) return D3F_OK;
+    D3F_REQUIRE(x && idx && out, D3F_ERR_INVALID, "null pointer");
+    auto kern = idx_is_64 ? gr_forward_kernel<true> : gr_forward_kernel<false>;
+    kern<<<d3f_ceil_div(n_rows, 8), 256, 0, stream>>>(x, idx, (long long)idx_stride, n_rows, n_supports, channels, out);
+    D3F_CHECK_LAUNCH();
+    return D3F_OK;
+}
+
+extern "C" int d3f_gather_rows_backward(const float* grad_out, const void* idx, int idx_is_64, int64_t idx_stride,
+                                        int n_rows, int n_supports, int channels, float* grad_x, d3f_stream stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    D3F_REQUIRE(n_rows >= 0 && n_supports >= 0 && channels >= 1, D3F_ERR_INVALID, "bad sizes");
+    if (n_supports > 0) {
+        D3F_REQUIRE(grad_x, D3F_ERR_INVALID, "null pointer");
+        D3F_CHECK_CUDA(cudaMemsetAsync(grad_x, 0, sizeof(float) * (size_t)n_supports * channels, stream));
+    }
+    if (n_rows == 0 || n_supports == 0) return D3F_OK;
+    D3F_REQUIRE(grad_out && idx, D3F_ERR_INVALID, "null pointer");
+    auto kern = idx_is_64 ? gr_backward_kernel<true> : gr_backward_kernel<false>;
+    kern<<<d3f_ceil_div(n_rows, 8), 256, 0, stream>>>(grad_out, idx, (long long)idx_stride, n_rows, n_supports, channels, grad_x);
+    D3F_CHECK_LAUNCH();
+    return D3F_OK;
+}
+
+extern "C" int d3f_detection_scores_forward(const float* features, const void* neighbors, int idx_is_64,
+                                            int64_t ld_inds, int n_points, int n_neighbors, int channels,
+                                            int eval_mode, float* scores, void* gmax_state, d3f_stream stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    D3F_REQUIRE(n_points >= 0 && n_neighbors >= 0, D3F_ERR_INVALID, "bad sizes");
+    D3F_REQUIRE(channels >= 1 && channels <= 32, D3F_ERR_UNSUPPORTED, "detection scores support up to 32 channels");
+    D3F_REQUIRE(gmax_state, D3F_ERR_INVALID, "null gmax_state");
+    D3F_CHECK_CUDA(cudaMemsetAsync(gmax_state, 0, 16, stream));
+    if (n_points == 0) return D3F_OK;
+    D3F_REQUIRE(features && (neighbors || n_neighbors == 0) && scores, D3F_ERR_INVALID, "null pointer");
+    D3F_REQUIRE((size_t)n_points * channels < 0xFFFFFFFFull, D3F_ERR_UNSUPPORTED, "too many feature elements");
+    ds_gmax_kernel<<<296, 256, 0, stream>>>(features, (size_t)n_points * channels, (unsigned long long*)gmax_state);
+    D3F_CHECK_LAUNCH();
+    auto kern = idx_is_64 ? ds_kernel<true, false> : ds_kernel<false, false>;
+    kern<<<d3f_ceil_div(n_points, 8), 256, 0, stream>>>(features, neighbors, (long long)ld_inds, n_points, n_neighbors,
+                                                       channels, (const unsigned long long*)gmax_state, eval_mode,
+                                                       scores, nullptr, nullptr, nullptr);
+    D3F_CHECK_LAUNCH();
+    return D3F_OK;
+}
+
+extern "C" int d3f_detection_scores_backward(const float* features, const void* neighbors, int idx_is_64,
+                                             int64_t ld_inds, int n_points, int n_neighbors, int channels,
+                                             int eval_mode, const void* gmax_state, const float* grad_scores,
+                                             float* grad_features, d3f_stream stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    D3F_REQUIRE(n_points >= 0 && n_neighbors >= 0, D3F_ERR_INVALID, "bad sizes");
+    D3F_REQUIRE(channels >= 1 && channels <= 32, D3F_ERR_UNSUPPORTED, "detection scores support up to 32 channels");
+    if (n_points == 0) return D3F_OK;
+    D3F_REQUIRE(features && (neighbors || n_neighbors == 0) && gmax_state && grad_scores && grad_features,
+                D3F_ERR_INVALID, "null pointer");
+    D3F_CHECK_CUDA(cudaMemsetAsync(grad_features, 0, sizeof(float) * (size_t)n_points * channels, stream));
+    float* gacc = (float*)((char*)gmax_state + 8);  // second 8 bytes of the state: dL/dgmax accumulator
+    D3F_CHECK_CUDA(cudaMemsetAsync(gacc, 0, 8, stream));
+    auto kern = idx_is_64 ? ds_kernel<true, true> : ds_kernel<false, true>;
+    kern<<<d3f_ceil_div(n_points, 8), 256, 0, stream>>>(features, neighbors, (long long)ld_inds, n_points, n_neighbors,
+                                                       channels, (const unsigned long long*)gmax_state, eval_mode,
+                                                       nullptr, grad_scores, grad_features, gacc);
+    D3F_CHECK_LAUNCH();
+    ds_gmax_backward_kernel<<<1, 1, 0, stream>>>((const unsigned long long*)gmax_state, gacc, grad_features);
+    D3F_CHECK_LAUNCH();
+    return D3F_OK;
+}

@@ -256,3 +256,124 @@ def pair_loss_backward(saved, kind, metric, safe_radius, pos_margin, neg_margin,
                                           _p(dists), _p(aux), _p(grad_losses.contiguous()), _p(ga), _p(gp), _p(gsa), _p(gsp),
                                           _stream()))
     return ga, gp, gsa, gsp
+
+
+# --------------------------------------------------------------------------- pooling / gathers / detection scores
+def _idx(t, name):
+    if not t.is_cuda:
+        raise RuntimeError("d3feat.pytorch_b200: `%s` must be a CUDA tensor" % name)
+    if t.dtype not in (torch.int32, torch.int64):
+        t = t.long()
+    return t
+
+
+class _MaxPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, inds):
+        lib = _lib.load()
+        x, inds = _cuda_f32(x, "x"), _idx(inds, "inds")
+        if inds.stride(-1) != 1:
+            inds = inds.contiguous()
+        nq, H = inds.shape
+        ns, C = x.shape
+        out = torch.empty((nq, C), dtype=torch.float32, device=x.device)
+        arg = torch.empty((nq, C), dtype=torch.int32, device=x.device)
+        global launch_count
+        launch_count += 1
+        with _Timed(("max_pool", nq, ns, H, C)):
+            _lib.check(lib.d3f_max_pool_forward(_p(x), _p(inds), 1 if inds.dtype == torch.int64 else 0,
+                                                inds.stride(0) if H > 0 else 0, nq, ns, H, C, _p(out), _p(arg), _stream()))
+        ctx.save_for_backward(arg)
+        ctx.shape = (nq, ns, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        (arg,) = ctx.saved_tensors
+        nq, ns, C = ctx.shape
+        g = _cuda_f32(g, "grad")
+        gx = torch.empty((ns, C), dtype=torch.float32, device=g.device)
+        with _Timed(("max_pool_bwd", nq, ns, C)):
+            _lib.check(lib.d3f_max_pool_backward(_p(g), _p(arg), nq, ns, C, _p(gx), _stream()))
+        return gx, None
+
+
+class _GatherRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, idx):
+        lib = _lib.load()
+        x, idx = _cuda_f32(x, "x"), _idx(idx, "idx")
+        if idx.dim() != 1:
+            raise RuntimeError("gather_rows expects a 1-D index (a strided column view is fine)")
+        m = idx.shape[0]
+        ns, C = x.shape
+        out = torch.empty((m, C), dtype=torch.float32, device=x.device)
+        global launch_count
+        launch_count += 1
+        with _Timed(("gather_rows", m, ns, C)):
+            _lib.check(lib.d3f_gather_rows_forward(_p(x), _p(idx), 1 if idx.dtype == torch.int64 else 0,
+                                                   idx.stride(0) if m > 0 else 1, m, ns, C, _p(out), _stream()))
+        ctx.save_for_backward(idx)
+        ctx.shape = (m, ns, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        (idx,) = ctx.saved_tensors
+        m, ns, C = ctx.shape
+        g = _cuda_f32(g, "grad")
+        gx = torch.empty((ns, C), dtype=torch.float32, device=g.device)
+        with _Timed(("gather_rows_bwd", m, ns, C)):
+            _lib.check(lib.d3f_gather_rows_backward(_p(g), _p(idx), 1 if idx.dtype == torch.int64 else 0,
+                                                    idx.stride(0) if m > 0 else 1, m, ns, C, _p(gx), _stream()))
+        return gx, None
+
+
+class _DetectionScores(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, neighbors, eval_mode):
+        lib = _lib.load()
+        feats, neighbors = _cuda_f32(feats, "features"), _idx(neighbors, "neighbors")
+        if neighbors.stride(-1) != 1:
+            neighbors = neighbors.contiguous()
+        n, C = feats.shape
+        H = neighbors.shape[1]
+        scores = torch.empty((n, 1), dtype=torch.float32, device=feats.device)
+        state = torch.empty(16, dtype=torch.uint8, device=feats.device)
+        global launch_count
+        launch_count += 1
+        with _Timed(("det_scores", n, H, C)):
+            _lib.check(lib.d3f_detection_scores_forward(_p(feats), _p(neighbors), 1 if neighbors.dtype == torch.int64 else 0,
+                                                        neighbors.stride(0) if H > 0 else 0, n, H, C, int(eval_mode),
+                                                        _p(scores), _p(state), _stream()))
+        ctx.save_for_backward(feats, neighbors, state)
+        ctx.eval_mode = int(eval_mode)
+        return scores
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        feats, neighbors, state = ctx.saved_tensors
+        n, C = feats.shape
+        H = neighbors.shape[1]
+        g = _cuda_f32(g.reshape(-1), "grad")
+        gf = torch.empty_like(feats)
+        with _Timed(("det_scores_bwd", n, H, C)):
+            _lib.check(lib.d3f_detection_scores_backward(_p(feats), _p(neighbors), 1 if neighbors.dtype == torch.int64 else 0,
+                                                         neighbors.stride(0) if H > 0 else 0, n, H, C, ctx.eval_mode,
+                                                         _p(state), _p(g), _p(gf), _stream()))
+        return gf, None, None
+
+
+def max_pool(x, inds):
+    return _MaxPool.apply(x, inds)
+
+
+def gather_rows(x, idx):
+    return _GatherRows.apply(x, idx)
+
+
+def detection_scores(feats, neighbors, eval_mode):
+    return _DetectionScores.apply(feats, neighbors, eval_mode)

@@ -161,6 +161,36 @@ int d3f_pair_loss_backward(const float* anchor, const float* positive, int P, in
                            float* grad_anchor, float* grad_positive,
                            float* grad_anc_score, float* grad_pos_score, d3f_stream stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Gathers between the KPConv layers (they dominate a GPU training step
+ * when left to ATen advanced indexing).  Shadow index (>= n_supports) reads a zero row.
+ *
+ * max pool      : max_pool(x, inds) of models/blocks.py:94-110 (strided-block shortcut, MaxPoolBlock);
+ *                 argmax [Nq,C] i32 = winning support row per output (-1 = shadow) for the backward.
+ * gather rows   : closest_pool(x, inds) = x_pad[inds[:,0]] of blocks.py:79-91 (NearestUpsampleBlock) and the
+ *                 correspondence row-selects of trainer.py:91-94; idx is read with an element stride.
+ * detection     : KPFCNN.detection_scores (models/architectures.py:322-368), train (eval_mode=0) or test
+ *                 (eval_mode=1: exact-equality local-max gate); features [N,C<=32], neighbors [N,H];
+ *                 gmax_state: 16-byte device scratch written by forward and read by backward.
+ * Backward entry points fully overwrite their grad_* output.
+ */
+int d3f_max_pool_forward(const float* x, const void* inds, int idx_is_64, int64_t ld_inds, int n_queries,
+                         int n_supports, int n_neighbors, int channels, float* out, int32_t* argmax,
+                         d3f_stream stream);
+int d3f_max_pool_backward(const float* grad_out, const int32_t* argmax, int n_queries, int n_supports,
+                          int channels, float* grad_x, d3f_stream stream);
+int d3f_gather_rows_forward(const float* x, const void* idx, int idx_is_64, int64_t idx_stride, int n_rows,
+                            int n_supports, int channels, float* out, d3f_stream stream);
+int d3f_gather_rows_backward(const float* grad_out, const void* idx, int idx_is_64, int64_t idx_stride,
+                             int n_rows, int n_supports, int channels, float* grad_x, d3f_stream stream);
+int d3f_detection_scores_forward(const float* features, const void* neighbors, int idx_is_64, int64_t ld_inds,
+                                 int n_points, int n_neighbors, int channels, int eval_mode, float* scores,
+                                 void* gmax_state, d3f_stream stream);
+int d3f_detection_scores_backward(const float* features, const void* neighbors, int idx_is_64, int64_t ld_inds,
+                                  int n_points, int n_neighbors, int channels, int eval_mode,
+                                  const void* gmax_state, const float* grad_scores, float* grad_features,
+                                  d3f_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,8 +40,10 @@ def test_kpfcnn_pair_vs_reference_fixture(cuda, name, kw, limits):
     feats, scores = model(batch)
     c = batch["corr"].long()
     n0 = int(batch["stack_lengths"][0][0])
-    o = PairLoss("circle", "euclidean", 10, 0.1, 0.1, 1.4)(feats[c[:, 0]], feats[c[:, 1] + n0], batch["dist_keypts"],
-                                                          scores[c[:, 0]], scores[c[:, 1] + n0])
+    from d3feat.pytorch_b200.blocks import gather
+    ia, ip = c[:, 0], c[:, 1] + n0
+    o = PairLoss("circle", "euclidean", 10, 0.1, 0.1, 1.4)(gather(feats, ia), gather(feats, ip), batch["dist_keypts"],
+                                                          gather(scores, ia), gather(scores, ip))
     (o["desc_loss"] + o["det_loss"]).backward()
     gn = {k: float(p.grad.norm()) for k, p in model.named_parameters() if p.grad is not None}
     errs = dict(features=rel_err(feats.detach().cpu(), g["features"]), scores=rel_err(scores.detach().cpu(), g["scores"]),
