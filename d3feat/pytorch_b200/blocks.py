@@ -191,6 +191,10 @@ class UnaryBlock(nn.Module):
             self.leaky_relu = nn.LeakyReLU(0.1)
 
     def forward(self, x, batch=None):
+        if not self.use_bn and x.is_cuda:
+            # Linear + learned bias (+ LeakyReLU 0.1) as one tensor-core GEMM with a fused epilogue
+            return ops.fused_linear(x, self.mlp.weight, self.mlp.bias + self.batch_norm.bias,
+                                    None if self.no_relu else 0.1)
         x = self.batch_norm(self.mlp(x))
         return x if self.no_relu else self.leaky_relu(x)
 
@@ -209,6 +213,8 @@ class LastUnaryBlock(nn.Module):
         self.mlp = nn.Linear(in_dim, out_dim, bias=True)
 
     def forward(self, x, batch=None):
+        if x.is_cuda:
+            return ops.fused_linear(x, self.mlp.weight, self.mlp.bias, None)
         return self.mlp(x)
 
     def __repr__(self):

@@ -15,6 +15,7 @@
 //                   out = diag(inv_n) wf W,  dwf = diag(inv_n) g W^T,  dW = wf^T diag(inv_n) g
 //   kp_scatter    : one warp per query: dx[idx] += sum_k w dwf  (+ kernel-point / modulation grads)
 #include "common.cuh"
+#include "gemm.cuh"
 
 namespace {
 
@@ -532,7 +533,8 @@ extern "C" int d3f_kpconv_forward(const float* q_pts, const float* s_pts, const 
     const int grid = d3f_ceil_div(nq, warps);
     KP_DISPATCH_ALL(kp_correlate_kernel, a, wf, wf_unmod, inv_n, deformed ? min_d2 : nullptr);
     D3F_CHECK_LAUNCH();
-    return kp_gemm<false, false>(nq, cout, K * cin, wf, K * cin, weights, cout, out, cout, inv_n, nullptr, stream);
+    D3fGemm g{nq, cout, K * cin, wf, K * cin, weights, cout, out, cout, inv_n, nullptr, nullptr, 0, 0.f, 0};
+    return d3f_gemm_launch(g, false, false, stream);
 }
 
 extern "C" int d3f_kpconv_backward(const float* q_pts, const float* s_pts, const void* inds, int idx_is_64,
@@ -560,13 +562,17 @@ extern "C" int d3f_kpconv_backward(const float* q_pts, const float* s_pts, const
     const int KC = K * cin;
     // dW[kc, o] = sum_i wf[i, kc] * inv_n[i] * g[i, o]
     if (grad_weights) {
-        rc = kp_gemm<true, false>(KC, cout, nq, wf, KC, grad_out, cout, grad_weights, cout, nullptr, inv_n, stream);
+        D3fGemm g{KC, cout, nq, wf, KC, grad_out, cout, grad_weights, cout, nullptr, inv_n, nullptr, 0, 0.f, 0};
+        rc = d3f_gemm_launch(g, true, false, stream);
         if (rc) return rc;
     }
     const bool need_scatter = grad_x || (deformed && (grad_kernel_points || grad_modulations));
     if (!need_scatter) return D3F_OK;
     // dwf[i, kc] = inv_n[i] * sum_o g[i, o] * W[kc, o]
-    rc = kp_gemm<false, true>(nq, KC, cout, grad_out, cout, weights, cout, w.dwf, KC, inv_n, nullptr, stream);
+    {
+        D3fGemm g{nq, KC, cout, grad_out, cout, weights, cout, w.dwf, KC, inv_n, nullptr, nullptr, 0, 0.f, 0};
+        rc = d3f_gemm_launch(g, false, true, stream);
+    }
     if (rc) return rc;
     if (ns > 0) {
         kp_rowpos_kernel<<<d3f_ceil_div(ns, 8), 256, 0, stream>>>(x, ns, cin, w.rowpos);

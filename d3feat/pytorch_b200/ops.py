@@ -377,3 +377,52 @@ def gather_rows(x, idx):
 
 def detection_scores(feats, neighbors, eval_mode):
     return _DetectionScores.apply(feats, neighbors, eval_mode)
+
+
+# --------------------------------------------------------------------------- tensor-core GEMM (3xTF32) + fused linear
+def gemm(a, b, trans_a=False, trans_b=False, row_scale=None, k_scale=None, bias=None, slope=None):
+    """C = act(row_scale * opA(a) @ (k_scale * opB(b)) + bias) via d3f_gemm (fp32-accurate tensor-core GEMM).
+    a: [M,K] (or [K,M] if trans_a); b: [K,N] (or [N,K] if trans_b)."""
+    lib = _lib.load()
+    a, b = _cuda_f32(a, "a"), _cuda_f32(b, "b")
+    M, K = (a.shape[1], a.shape[0]) if trans_a else (a.shape[0], a.shape[1])
+    N = b.shape[0] if trans_b else b.shape[1]
+    kb = b.shape[1] if trans_b else b.shape[0]
+    if kb != K:
+        raise RuntimeError("gemm: inner dimensions differ (%d vs %d)" % (K, kb))
+    c = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    global launch_count
+    launch_count += 1
+    with _Timed(("gemm", M, N, K, bool(trans_a), bool(trans_b))):
+        _lib.check(lib.d3f_gemm(int(trans_a), int(trans_b), M, N, K, _p(a), a.stride(0), _p(b), b.stride(0), _p(c), N,
+                                _p(None if row_scale is None else _cuda_f32(row_scale, "row_scale")),
+                                _p(None if k_scale is None else _cuda_f32(k_scale, "k_scale")),
+                                _p(None if bias is None else _cuda_f32(bias, "bias")),
+                                0 if slope is None else 1, 0.0 if slope is None else float(slope), _stream()))
+    return c
+
+
+class _FusedLinear(torch.autograd.Function):
+    """y = LeakyReLU_slope(x @ W^T + b)  (slope None: no activation) -- the UnaryBlock body
+    (models/blocks.py:505-510 with use_bn=False) as one GEMM with a fused epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, slope):
+        y = gemm(x, weight, trans_b=True, bias=bias, slope=slope)
+        ctx.save_for_backward(x, weight, y if slope is not None else None)
+        ctx.slope = slope
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight, y = ctx.saved_tensors
+        dz = gy if y is None else gy * torch.where(y > 0, 1.0, float(ctx.slope))
+        dz = dz.contiguous()
+        dx = gemm(dz, weight) if ctx.needs_input_grad[0] else None                 # [M,out] @ [out,in]
+        dw = gemm(dz, x, trans_a=True) if ctx.needs_input_grad[1] else None         # dz^T [out,M] @ x [M,in]
+        db = dz.sum(dim=0) if ctx.needs_input_grad[2] else None
+        return dx, dw, db, None
+
+
+def fused_linear(x, weight, bias, slope=None):
+    return _FusedLinear.apply(x, weight, bias, slope)

@@ -191,6 +191,17 @@ int d3f_detection_scores_backward(const float* features, const void* neighbors, 
                                   const void* gmax_state, const float* grad_scores, float* grad_features,
                                   d3f_stream stream);
 
+/* ------------------------------------------------------------------------------------------
+ * fp32-accurate tensor-core GEMM (3xTF32) with fused epilogue -- the dense contraction behind KPConv
+ * (blocks.py:369-380) and the UnaryBlock Linear + bias + LeakyReLU (blocks.py:481-515):
+ *   C[M,N] = act( row_scale[m] * sum_k opA(m,k) * k_scale[k] * opB(k,n) + bias[n] )
+ *   trans_a: A stored [K,M] else [M,K];  trans_b: B stored [N,K] else [K,N]  (row-major, lda/ldb/ldc in elements)
+ *   row_scale / k_scale / bias may be NULL; k_scale needs trans_b == 0; leaky_relu != 0 applies max(v, slope*v).
+ */
+int d3f_gemm(int trans_a, int trans_b, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+             float* C, int ldc, const float* row_scale, const float* k_scale, const float* bias,
+             int leaky_relu, float slope, d3f_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,59 @@
+"""The 3xTF32 tensor-core GEMM must be fp32-accurate (plain TF32 would eat the 1e-4 budget)."""
+import numpy as np
+import pytest
+import torch
+
+from _util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (127, 65, 33), (128, 64, 32), (300, 45, 15), (1000, 512, 960),
+                                   (190, 512, 7680), (480, 32, 40000), (4097, 33, 130)])
+def test_gemm_matches_fp64(cuda, ta, tb, M, N, K):
+    from d3feat.pytorch_b200 import ops
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    A = rng.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
+    B = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+    rs = (rng.random(M) + 0.5).astype(np.float32)
+    ks = (rng.random(K) + 0.5).astype(np.float32) if not tb else None
+    opA = A.T.astype(np.float64) if ta else A.astype(np.float64)
+    opB = B.T.astype(np.float64) if tb else B.astype(np.float64)
+    ref = rs[:, None] * (opA @ ((ks[:, None].astype(np.float64) if ks is not None else 1.0) * opB))
+    got = ops.gemm(torch.from_numpy(A).to(cuda), torch.from_numpy(B).to(cuda), ta, tb,
+                   row_scale=torch.from_numpy(rs).to(cuda), k_scale=None if ks is None else torch.from_numpy(ks).to(cuda))
+    # fp32 accuracy: error relative to |A||B| row/col magnitudes ~ sqrt(K) * 2^-23
+    assert rel_err(got.cpu(), ref) < 2e-6 * max(1.0, np.sqrt(K) / 8), (M, N, K)
+
+
+def test_gemm_handles_strided_rows_and_bias_activation(cuda):
+    from d3feat.pytorch_b200 import ops
+    rng = np.random.default_rng(3)
+    X = torch.from_numpy(rng.standard_normal((500, 70)).astype(np.float32)).to(cuda)
+    W = torch.from_numpy(rng.standard_normal((48, 70)).astype(np.float32)).to(cuda)
+    b = torch.from_numpy(rng.standard_normal(48).astype(np.float32)).to(cuda)
+    ref = torch.nn.functional.leaky_relu(X.double() @ W.double().t() + b.double(), 0.1)
+    got = ops.gemm(X, W, trans_b=True, bias=b, slope=0.1)
+    assert rel_err(got.cpu(), ref.cpu()) < 2e-6
+
+
+def test_fused_linear_autograd(cuda):
+    from d3feat.pytorch_b200 import ops
+    rng = np.random.default_rng(4)
+    x = torch.from_numpy(rng.standard_normal((777, 96)).astype(np.float32))
+    w = torch.from_numpy((rng.standard_normal((40, 96)) / 10).astype(np.float32))
+    b = torch.from_numpy(rng.standard_normal(40).astype(np.float32))
+    g = torch.from_numpy(rng.standard_normal((777, 40)).astype(np.float32))
+    for slope in (0.1, None):
+        xr, wr, br = (t.double().requires_grad_(True) for t in (x, w, b))
+        y = xr @ wr.t() + br
+        if slope is not None:
+            y = torch.nn.functional.leaky_relu(y, slope)
+        (y * g.double()).sum().backward()
+        xg, wg, bg = (t.to(cuda).requires_grad_(True) for t in (x, w, b))
+        out = ops.fused_linear(xg, wg, bg, slope)
+        (out * g.to(cuda)).sum().backward()
+        assert rel_err(out.detach().cpu(), y.detach()) < 2e-6
+        assert rel_err(xg.grad.cpu(), xr.grad) < 2e-6 and rel_err(wg.grad.cpu(), wr.grad) < 5e-6
+        assert rel_err(bg.grad.cpu(), br.grad) < 2e-6
