@@ -28,6 +28,15 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
+# Keep stdout for the ONE JSON line: everything else (NCCL banners, warnings) goes to stderr.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
 N_POINTS = 20000
 POOL = 4  # distinct synthetic pairs cycled through the steps (per rank)
 
@@ -41,6 +50,8 @@ def parse():
     ap.add_argument("--points", type=int, default=N_POINTS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fwd-only", action="store_true", help="diagnostic: forward + loss only")
+    ap.add_argument("--host-profile", action="store_true", help="diagnostic: CPU enqueue time per phase -> stderr")
+    ap.add_argument("--no-graph", action="store_true", help="diagnostic: static pipeline without CUDA-graph capture")
     return ap.parse_args()
 
 
@@ -187,7 +198,7 @@ def run_reference(args):
                              "sample": sample, "stage_seconds_per_pair": {k: v / args.steps for k, v in stages.items()}},
             "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 LIMITS_20K = [35, 42, 42, 45, 47]  # 80th-percentile rule on the synthetic 20k pairs (recomputed on the device below)
@@ -212,6 +223,7 @@ def run_b200(args):
     from d3feat.pytorch_b200.dataloader import calibrate_neighbors, collate_fn_descriptor
     from d3feat.pytorch_b200.loss import PairLoss
     from d3feat.pytorch_b200 import parallel
+    from d3feat.pytorch_b200.engine import PairStep, plan_capacities
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -245,9 +257,19 @@ def run_b200(args):
     h2d = sum(t.numel() * t.element_size() for t in host[0])
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    hp = {}
+
+    def tick(name, t0):
+        if args.host_profile:
+            hp[name] = hp.get(name, 0.0) + time.perf_counter() - t0
+        return time.perf_counter()
+
     def step(data, read_loss):
+        t0 = time.perf_counter()
         batch = collate_fn_descriptor([data], cfg, limits)
+        t0 = tick("collate", t0)
         feats, scores = model(batch)
+        t0 = tick("forward", t0)
         c = batch["corr"].long()
         n0 = data[0].shape[0]
         ia, ip = c[:, 0], c[:, 1] + n0
@@ -258,17 +280,42 @@ def run_b200(args):
         else:
             out = loss_fn(a, p, batch["dist_keypts"], sa, sp)
         loss = out["desc_loss"] * cfg.desc_loss_weight + out["det_loss"] * cfg.det_loss_weight
+        t0 = tick("loss", t0)
         if not args.fwd_only:
             flat.zero()
             loss.backward()
+            t0 = tick("backward", t0)
             flat.allreduce()
             opt.step()
+            t0 = tick("optimizer", t0)
         return float(loss.detach()) if read_loss else loss
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # ---- the production path: static capacities, no host sync, one CUDA graph per pair step
+    sizes = [[int(t.shape[0]) for t in collate_fn_descriptor([p], cfg, limits)["points"]] for p in pairs]
+    caps = plan_capacities(sizes)
+    stepper = PairStep(model, cfg, limits, caps, args.points, args.points, loss_fn,
+                       None if args.fwd_only else opt, None if args.fwd_only else flat, num_node=cfg.num_node,
+                       cross_fragment=parallel.cross_fragment_loss if world > 1 else None)
+    l0 = lib.d3f_launch_count()
+    stepper(devp[0])
+    torch.cuda.synchronize()
+    launches_per_step = lib.d3f_launch_count() - l0
+    graph_mode = "cuda-graph"
+    if args.no_graph:
+        graph_mode = "eager (static shapes)"
+    else:
+        try:
+            stepper.capture()
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write("CUDA graph capture failed (%s: %s); running the static pipeline eagerly\n" % (type(e).__name__, e))
+            stepper.graph = None
+            graph_mode = "eager (static shapes; capture failed)"
+            torch.cuda.synchronize()
 
     def timed(kind, steps, profile=False):
         src = devp if kind == "device" else host
@@ -281,7 +328,12 @@ def run_b200(args):
             flush.fill_(i & 0xFF)          # L2 flush, outside the event bracket
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            step(src[i % POOL], read_loss=(kind == "host"))
+            if profile:
+                step(src[i % POOL], read_loss=False)        # exact-shape eager path with per-op events
+            else:
+                stepper(src[i % POOL])                      # H2D (e2e) or D2D copies into the static inputs + replay
+                if kind == "host":
+                    float(stepper.loss)                     # D2H read of the step's result
             e1.record()
             evs.append((e0, e1))
         barrier()
@@ -294,15 +346,21 @@ def run_b200(args):
         return float(t[0]), wall, lib.d3f_launch_count() - launches0, prof
 
     for i in range(max(args.warmup, 3)):
-        step(devp[i % POOL], False)
+        stepper(devp[i % POOL])
     for i in range(2):
-        step(host[i % POOL], True)
+        stepper(host[i % POOL]); float(stepper.loss)
+    stepper.check()
+    for i in range(2):
+        step(devp[i % POOL], False)
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev, wall_dev, launches, _ = timed("device", args.steps)
+    hp.clear()
+    ms_dev, wall_dev, _, _ = timed("device", args.steps)
     ms_e2e, wall_e2e, _, _ = timed("host", args.steps)
+    stepper.check()                  # no capacity / candidate-buffer overflow in any timed step
+    launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
     # separate pass with per-op CUDA events (same steps, same stream) for the roofline / op breakdown only
     _, _, _, prof = timed("device", args.steps, profile=True)
@@ -312,6 +370,9 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
+    if args.host_profile:
+        n_calls = 2 * args.steps + args.steps
+        sys.stderr.write("host enqueue ms/step (timed passes only approx): %s\n" % {k: round(1e3 * v / max(n_calls, 1), 3) for k, v in hp.items()})
     pk, pk_src = peaks()
     # roofline of the dominant op: the KPConv forward with the most algorithmic bytes (L0 resnetb 32->32)
     fwd = {k: v for k, v in prof.items() if k[0] == "kpconv_fwd"}
@@ -352,9 +413,11 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, limits),
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4 + 17 * 8,
-                    "api": "collate_fn_descriptor(pinned host tensors) -> KPFCNN -> PairLoss -> backward -> SGD -> float(loss)"},
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                    "api": "engine.PairStep(pinned host tensors): H2D -> [pyramid build -> KPFCNN -> PairLoss -> backward -> SGD] "
+                           "as one CUDA graph -> float(loss)"},
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
+            "execution": {"mode": graph_mode, "capacities": caps, "final_loss": float(stepper.loss)},
             "wall_s": {"device": wall_dev, "e2e": wall_e2e},
             "roofline": roofline}
 
@@ -377,7 +440,7 @@ def run_b200(args):
                                 "sample": "%d pairs of the same workload (pyramid: reference C++ via oracle/_ref, single thread as "
                                           "in the reference; model+loss+bwd+SGD: torch-CPU oracle on %d threads = fastest of {8,16,32,64,all %d})" % (n_cpu, cores, os.cpu_count() or 1),
                                 "stage_seconds_per_pair": {k: v / n_cpu for k, v in stages.items()}}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

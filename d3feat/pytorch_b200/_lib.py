@@ -26,9 +26,9 @@ SIGNATURES = {
     "d3f_last_error_string": (ctypes.c_char_p, []),
     "d3f_launch_count": (ctypes.c_ulonglong, []),
     "d3f_radius_neighbors_workspace_bytes": (c_sz, [c_i, c_i, c_i]),
-    "d3f_radius_neighbors": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_i, c_p, c_i, c_p, c_i, c_p, c_sz, c_p]),
+    "d3f_radius_neighbors": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_f, c_i, c_p, c_i, c_i, c_p, c_i, c_p, c_sz, c_p]),
     "d3f_grid_subsample_workspace_bytes": (c_sz, [c_i, c_i]),
-    "d3f_grid_subsample": (c_i, [c_p, c_p, c_i, c_i, c_f, c_p, c_p, c_p, c_sz, c_p]),
+    "d3f_grid_subsample": (c_i, [c_p, c_p, c_i, c_i, c_f, c_p, c_i, c_p, c_p, c_sz, c_p]),
     "d3f_kpconv_workspace_bytes": (c_sz, [c_i] * 6),
     "d3f_kpconv_forward": (c_i, [c_p, c_p, c_p, c_i, c_i64, c_p, c_p, c_p, c_i, c_p,
                                  c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_i,

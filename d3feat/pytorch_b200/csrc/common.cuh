@@ -60,7 +60,8 @@ __device__ __forceinline__ uint32_t d3f_hash64(uint64_t k) {
 
 #define D3F_EMPTY_KEY 0xFFFFFFFFFFFFFFFFULL
 
-// batch element of stacked row i given per-element lengths (n_batch is tiny)
+// batch element of stacked row i given per-element lengths (n_batch is tiny); -1 if i >= sum(len):
+// buffers may be allocated larger than the real row count (static capacities for CUDA-graph capture)
 __device__ __forceinline__ int d3f_batch_of(int i, const int32_t* __restrict__ len, int nb, int* start) {
     int s = 0;
     for (int b = 0; b < nb; ++b) {
@@ -69,5 +70,5 @@ __device__ __forceinline__ int d3f_batch_of(int i, const int32_t* __restrict__ l
         s += l;
     }
     *start = s;
-    return nb - 1;
+    return -1;   // row i lies beyond the real rows (capacity padding)
 }

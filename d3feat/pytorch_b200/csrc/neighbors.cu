@@ -36,6 +36,7 @@ __global__ void nb_insert_kernel(const float* __restrict__ s, const int32_t* __r
     if (i >= ns) return;
     int st;
     int b = d3f_batch_of(i, s_len, nb, &st);
+    if (b < 0) return;  // capacity padding
     uint64_t key = cell_key(b, cell_coord(s[3 * i], inv_cs), cell_coord(s[3 * i + 1], inv_cs),
                             cell_coord(s[3 * i + 2], inv_cs));
     uint32_t slot = d3f_hash64(key) & mask;
@@ -70,11 +71,14 @@ __global__ void nb_alloc_kernel(const uint32_t* __restrict__ cnt, uint32_t* star
     if (t < table) start[t] = base + incl - c;
 }
 
-__global__ void nb_scatter_kernel(const float* __restrict__ s, int ns, const uint32_t* __restrict__ slot_of,
+__global__ void nb_scatter_kernel(const float* __restrict__ s, int ns, const int32_t* __restrict__ s_len, int nb,
+                                  const uint32_t* __restrict__ slot_of,
                                   const uint32_t* __restrict__ rank, const uint32_t* __restrict__ start,
                                   float4* sorted) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ns) return;
+    int st;
+    if (d3f_batch_of(i, s_len, nb, &st) < 0) return;
     uint32_t dst = start[slot_of[i]] + rank[i];
     sorted[dst] = make_float4(s[3 * i], s[3 * i + 1], s[3 * i + 2], __int_as_float(i));
 }
@@ -84,7 +88,7 @@ __global__ void nb_query_kernel(const float* __restrict__ q, const int32_t* __re
                                 int ns, float inv_cs, float r2, const unsigned long long* __restrict__ keys,
                                 const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ start,
                                 uint32_t mask, const float4* __restrict__ sorted, int max_cols, void* out,
-                                int32_t* info, int cap) {
+                                int32_t* info, int cap, int pad_index) {
     extern __shared__ unsigned long long cand_all[];
     __shared__ int s_max, s_ovf;
     if (threadIdx.x == 0) { s_max = 0; s_ovf = 0; }
@@ -93,9 +97,16 @@ __global__ void nb_query_kernel(const float* __restrict__ q, const int32_t* __re
     const int qi = blockIdx.x * (blockDim.x >> 5) + warp;
     unsigned long long* cand = cand_all + (size_t)warp * cap;
     int count = 0;
-    if (qi < nq) {
-        int st;
-        const int b = d3f_batch_of(qi, q_len, nb, &st);
+    int st;
+    const int b = qi < nq ? d3f_batch_of(qi, q_len, nb, &st) : -1;
+    if (qi < nq && b < 0 && out != nullptr) {
+        // capacity padding row: no neighbours at all
+        for (int col = lane; col < max_cols; col += 32) {
+            if (IDX64) ((long long*)out)[(size_t)qi * max_cols + col] = pad_index;
+            else ((int*)out)[(size_t)qi * max_cols + col] = pad_index;
+        }
+    }
+    if (b >= 0) {
         const float qx = q[3 * qi], qy = q[3 * qi + 1], qz = q[3 * qi + 2];
         uint32_t beg = 0, n = 0;
         if (lane < 27 && ns > 0) {
@@ -157,7 +168,7 @@ __global__ void nb_query_kernel(const float* __restrict__ q, const int32_t* __re
                 }
             }
             for (int col = lane; col < max_cols; col += 32) {
-                const int v = col < m ? (int)(uint32_t)(cand[col] & 0xffffffffULL) : ns;
+                const int v = col < m ? (int)(uint32_t)(cand[col] & 0xffffffffULL) : pad_index;
                 if (IDX64) ((long long*)out)[(size_t)qi * max_cols + col] = v;
                 else ((int*)out)[(size_t)qi * max_cols + col] = v;
             }
@@ -203,7 +214,7 @@ extern "C" size_t d3f_radius_neighbors_workspace_bytes(int n_queries, int n_supp
 
 extern "C" int d3f_radius_neighbors(const float* queries, const float* supports, const int32_t* q_lengths,
                                     const int32_t* s_lengths, int n_batch, int n_queries, int n_supports,
-                                    float radius, int max_cols, void* out_idx, int idx_is_64,
+                                    float radius, int max_cols, void* out_idx, int idx_is_64, int pad_index,
                                     int32_t* out_info, int row_capacity, void* workspace,
                                     size_t workspace_bytes, d3f_stream stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -233,7 +244,7 @@ extern "C" int d3f_radius_neighbors(const float* queries, const float* supports,
         D3F_CHECK_LAUNCH();
         nb_alloc_kernel<<<d3f_ceil_div((int)w.table, T), T, 0, stream>>>(w.cnt, w.start, w.table, w.cursor);
         D3F_CHECK_LAUNCH();
-        nb_scatter_kernel<<<d3f_ceil_div(n_supports, T), T, 0, stream>>>(supports, n_supports, w.slot_of,
+        nb_scatter_kernel<<<d3f_ceil_div(n_supports, T), T, 0, stream>>>(supports, n_supports, s_lengths, n_batch, w.slot_of,
                                                                         w.rank, w.start, w.sorted);
         D3F_CHECK_LAUNCH();
     }
@@ -245,7 +256,7 @@ extern "C" int d3f_radius_neighbors(const float* queries, const float* supports,
         D3F_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<d3f_ceil_div(n_queries, warps), warps * 32, smem, stream>>>(
         queries, q_lengths, n_batch, n_queries, n_supports, inv_cs, r2, w.keys, w.cnt, w.start, w.table - 1,
-        w.sorted, max_cols, out_idx, out_info, row_capacity);
+        w.sorted, max_cols, out_idx, out_info, row_capacity, pad_index < 0 ? n_supports : pad_index);
     D3F_CHECK_LAUNCH();
     // info[2] = occupied cells (diagnostic)
     D3F_CHECK_CUDA(cudaMemcpyAsync(out_info + 2, w.cursor + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));

@@ -92,6 +92,7 @@ __global__ void sub_insert_kernel(const float* __restrict__ p, const int32_t* __
     if (i >= n) return;
     int st;
     const int b = d3f_batch_of(i, len, nb, &st);
+    if (b < 0) return;  // capacity padding
     const SubGrid g = grid[b];
     // grid_subsampling.cpp:53-56
     const unsigned long long ix = (unsigned long long)floorf(__fdiv_rn(__fsub_rn(p[3 * (size_t)i], g.ox), dl));
@@ -128,10 +129,13 @@ __global__ void sub_alloc_kernel(const uint32_t* __restrict__ cnt, uint32_t* sta
     if (t < table) start[t] = base + incl - c;
 }
 
-__global__ void sub_scatter_kernel(int n, const uint32_t* __restrict__ slot_of, const uint32_t* __restrict__ rank,
+__global__ void sub_scatter_kernel(int n, const int32_t* __restrict__ len, int nb, const uint32_t* __restrict__ slot_of,
+                                   const uint32_t* __restrict__ rank,
                                    const uint32_t* __restrict__ start, uint32_t* member) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    int st;
+    if (d3f_batch_of(i, len, nb, &st) < 0) return;
     member[start[slot_of[i]] + rank[i]] = (uint32_t)i;
 }
 
@@ -209,12 +213,10 @@ sub_order_kernel(const int32_t* __restrict__ len, int nb, const unsigned long lo
         const uint32_t s = slot_of[i];
         if (minidx[s] == (uint32_t)i) { cor[j] = s; ck[j] = keys[s] & KEY_MASK; ++j; }
     }
-    if (tid == 0) {
-        out_len[b] = (int32_t)M;
-        if (M > R20) atomicMax(&info[0], 2);  // more than 2^20 cells in one batch element
-    }
+    const bool bad = M > R20 || info[0] != 0;   // > 2^20 cells in one element, or voxel keys beyond 56 bits
+    if (tid == 0) out_len[b] = bad ? -1 : (int32_t)M;
     __syncthreads();
-    if (M == 0 || M > R20) return;
+    if (M == 0 || bad) return;
 
     // ---- unordered_map iteration order (closed form, one round per bucket count)
     uint32_t* seq = seq_all + st;
@@ -261,22 +263,40 @@ sub_order_kernel(const int32_t* __restrict__ len, int nb, const unsigned long lo
     }
 }
 
-__global__ void sub_emit_kernel(const int32_t* __restrict__ len, const int32_t* __restrict__ out_len, int nb,
+__global__ void sub_emit_kernel(const int32_t* __restrict__ len, int32_t* __restrict__ out_len, int nb,
                                 int n, const uint32_t* __restrict__ seq_all, const uint32_t* __restrict__ cell_of_rank,
-                                const float4* __restrict__ bary, float* out) {
+                                const float4* __restrict__ bary, float* out, int out_capacity) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (i == 0) {  // the caller's output buffer is too small: report it instead of writing out of bounds
+        long long tot = 0;
+        for (int e = 0; e < nb; ++e) tot += out_len[e] > 0 ? out_len[e] : 0;
+        if (tot > out_capacity) out_len[nb] = 1;   // out_lengths has n_batch + 1 entries: [n_batch] = overflow flag
+    }
+    if (i >= out_capacity) return;
     // i indexes the OUTPUT row; find its batch element from out_len
     int so = 0, si = 0, b = -1;
     for (int e = 0; e < nb; ++e) {
-        if (i < so + out_len[e]) { b = e; break; }
-        so += out_len[e];
+        const int ol = out_len[e] > 0 ? out_len[e] : 0;
+        if (i < so + ol) { b = e; break; }
+        so += ol;
         si += len[e];
     }
     if (b < 0) return;
     const uint32_t r = seq_all[si + (i - so)];
     const float4 v = bary[cell_of_rank[si + r]];
     out[3 * (size_t)i] = v.x; out[3 * (size_t)i + 1] = v.y; out[3 * (size_t)i + 2] = v.z;
+}
+
+// If the caller's output buffer was too small, clamp the reported lengths to the rows that were written so
+// that later stages never index past out_capacity (the overflow flag stays set in out_len[nb]).
+__global__ void sub_clamp_kernel(int32_t* out_len, int nb, int out_capacity) {
+    long long room = out_capacity;
+    for (int e = 0; e < nb; ++e) {
+        const long long l = out_len[e] > 0 ? out_len[e] : 0;
+        if (l > room) out_len[e] = (int32_t)room;
+        room -= l < room ? l : room;
+    }
 }
 
 struct SubWs {
@@ -328,14 +348,16 @@ extern "C" size_t d3f_grid_subsample_workspace_bytes(int n_points, int n_batch) 
 }
 
 extern "C" int d3f_grid_subsample(const float* points, const int32_t* lengths, int n_batch, int n_points,
-                                  float sample_dl, float* out_points, int32_t* out_lengths, void* workspace,
-                                  size_t workspace_bytes, d3f_stream stream_) {
+                                  float sample_dl, float* out_points, int out_capacity, int32_t* out_lengths,
+                                  void* workspace, size_t workspace_bytes, d3f_stream stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     D3F_REQUIRE(n_points >= 0 && n_batch >= 1 && n_batch < 256, D3F_ERR_INVALID, "bad sizes");
     D3F_REQUIRE(lengths && out_lengths, D3F_ERR_INVALID, "null lengths");
     D3F_REQUIRE(sample_dl > 0.f, D3F_ERR_INVALID, "sample_dl must be positive");
     D3F_REQUIRE(n_points < (1 << 30), D3F_ERR_UNSUPPORTED, "too many points");
-    D3F_CHECK_CUDA(cudaMemsetAsync(out_lengths, 0, n_batch * sizeof(int32_t), stream));
+    D3F_CHECK_CUDA(cudaMemsetAsync(out_lengths, 0, (n_batch + 1) * sizeof(int32_t), stream));
+    D3F_REQUIRE(out_capacity >= 0, D3F_ERR_INVALID, "bad out_capacity");
+    if (out_points && out_capacity > 0) D3F_CHECK_CUDA(cudaMemsetAsync(out_points, 0, sizeof(float) * 3 * (size_t)out_capacity, stream));
     if (n_points == 0) return D3F_OK;
     D3F_REQUIRE(points && out_points, D3F_ERR_INVALID, "null points");
     SubWs w;
@@ -354,7 +376,7 @@ extern "C" int d3f_grid_subsample(const float* points, const int32_t* lengths, i
     D3F_CHECK_LAUNCH();
     sub_alloc_kernel<<<d3f_ceil_div((int)w.table, T), T, 0, stream>>>(w.cnt, w.start, w.table, w.cursor);
     D3F_CHECK_LAUNCH();
-    sub_scatter_kernel<<<d3f_ceil_div(n_points, T), T, 0, stream>>>(n_points, w.slot_of, w.rank, w.start, w.member);
+    sub_scatter_kernel<<<d3f_ceil_div(n_points, T), T, 0, stream>>>(n_points, lengths, n_batch, w.slot_of, w.rank, w.start, w.member);
     D3F_CHECK_LAUNCH();
     sub_reduce_kernel<<<d3f_ceil_div((int)w.table, T), T, 0, stream>>>(points, lengths, n_batch, w.keys, w.cnt,
                                                                       w.start, w.slot_of, w.member, w.table, w.bary);
@@ -366,7 +388,9 @@ extern "C" int d3f_grid_subsample(const float* points, const int32_t* lengths, i
                                                               w.gbuf_stride, w.gft_stride, out_lengths, w.info);
     D3F_CHECK_LAUNCH();
     sub_emit_kernel<<<d3f_ceil_div(n_points, T), T, 0, stream>>>(lengths, out_lengths, n_batch, n_points, w.seq,
-                                                                w.cell_of_rank, w.bary, out_points);
+                                                                w.cell_of_rank, w.bary, out_points, out_capacity);
+    D3F_CHECK_LAUNCH();
+    sub_clamp_kernel<<<1, 1, 0, stream>>>(out_lengths, n_batch, out_capacity);
     D3F_CHECK_LAUNCH();
     return D3F_OK;
 }

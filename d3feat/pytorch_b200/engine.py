@@ -1,0 +1,198 @@
+"""Static-shape, sync-free execution of the whole hot path for one fragment pair, and its CUDA-graph
+capture.
+
+The drop-in API (dataloader.collate_fn_descriptor + KPFCNN + losses) sizes every tensor from data
+(numbers of sub-sampled points, neighbour-matrix widths), which costs ~17 host round trips per pair
+and ~700 eagerly launched kernels: on a B200 the step is then bound by the host, not the GPU.  This
+module runs the same kernels on CAPACITY-padded tensors instead:
+
+* level l of the pyramid is allocated with `caps[l]` rows (caps[0] = the real stacked size); the real
+  row counts live on the device (the `lengths` vectors the C ABI already takes);
+* padding query rows get all-shadow neighbour rows, padding support rows are never referenced, and
+  the shadow index of level l is `caps[l]` (d3f_radius_neighbors' `pad_index`), so every real row
+  computes exactly what it computes in the exact-shape pipeline;
+* nothing reads back to the host inside the step, so collate + forward + loss + backward + optimizer
+  is ONE `torch.cuda.CUDAGraph` replayed per pair; the overflow/validity flags of all kernels come back
+  in one small status tensor next to the loss.
+
+Neighbour matrices are int32 here (the kernels take either width).
+"""
+import math
+
+import torch
+
+from . import ops
+from .blocks import gather
+
+
+def plan_capacities(level_sizes, margin=1.10, align=64):
+    """caps[l] for l >= 1 from observed level sizes (list of per-pair lists); level 0 is exact."""
+    n_levels = len(level_sizes[0])
+    caps = [max(s[0] for s in level_sizes)]
+    for l in range(1, n_levels):
+        m = max(s[l] for s in level_sizes)
+        caps.append(int(math.ceil(m * margin / align) * align))
+    return caps
+
+
+def collate_static(pts0, pts1, feat0, feat1, corr, dist_keypts, config, limits, caps, lengths=None):
+    """Same pyramid as dataloader.collate_fn_descriptor (reference dataloader.py:69-189) on
+    capacity-padded tensors, with no host synchronisation.  Returns (batch dict, status int32 tensor);
+    status must be all zeros for the batch to be valid (checked by the caller after the step)."""
+    dev = pts0.device
+    points = torch.cat([pts0, pts1], dim=0)
+    feats = torch.cat([feat0, feat1], dim=0)
+    if lengths is None:  # (inside a CUDA-graph capture the caller passes a pre-built device tensor)
+        lengths = torch.tensor([pts0.shape[0], pts1.shape[0]], dtype=torch.int32, device=dev)
+    r_normal = config.first_subsampling_dl * config.conv_radius
+    arch = config.architecture
+    out = {'points': [], 'neighbors': [], 'pools': [], 'upsamples': [], 'stack_lengths': []}
+    flags = []
+    empty_idx = torch.zeros((0, 1), dtype=torch.int32, device=dev)
+    layer, layer_blocks = 0, []
+
+    def search(q, s, ql, sl, r, limit, pad):
+        idx, info = ops.radius_neighbors_raw(q, s, ql, sl, r, int(limit), torch.int32, None, False, pad_index=pad)
+        flags.append(info[1:2])           # 1 = a row overflowed the candidate buffer
+        return idx
+
+    for bi, block in enumerate(arch):
+        if 'global' in block or 'upsample' in block:
+            break
+        if not ('pool' in block or 'strided' in block):
+            layer_blocks.append(block)
+            if bi < len(arch) - 1 and 'upsample' not in arch[bi + 1]:
+                continue
+        cap = caps[layer]
+        if layer_blocks:
+            deform = any('deformable' in b for b in layer_blocks[:-1])
+            r = r_normal * config.deform_radius / config.conv_radius if deform else r_normal
+            conv_i = search(points, points, lengths, lengths, r, limits[layer], cap)
+        else:
+            conv_i = empty_idx
+        if 'pool' in block or 'strided' in block:
+            dl = 2 * r_normal / config.conv_radius
+            cap_next = caps[layer + 1]
+            pool_p, pool_len = ops.grid_subsample_raw(points, lengths, dl, cap_next)
+            flags.append(pool_len[2:3])                       # output capacity exceeded
+            flags.append((pool_len[:2] < 0).to(torch.int32))  # unsupported voxel grid
+            pool_b = pool_len[:2]
+            r = r_normal * config.deform_radius / config.conv_radius if 'deformable' in block else r_normal
+            pool_i = search(pool_p, points, pool_b, lengths, r, limits[layer], cap)
+            up_i = search(points, pool_p, lengths, pool_b, 2 * r, limits[layer], cap_next)
+        else:
+            pool_i, up_i = empty_idx, empty_idx
+            pool_p = torch.zeros((0, 3), dtype=torch.float32, device=dev)
+            pool_b = torch.zeros((0,), dtype=torch.int32, device=dev)
+        out['points'].append(points)
+        out['neighbors'].append(conv_i)
+        out['pools'].append(pool_i)
+        out['upsamples'].append(up_i)
+        out['stack_lengths'].append(lengths)
+        points, lengths = pool_p, pool_b
+        r_normal *= 2
+        layer += 1
+        layer_blocks = []
+    out['features'] = feats
+    out['corr'] = corr
+    out['dist_keypts'] = dist_keypts
+    return out, torch.cat(flags)
+
+
+class PairStep:
+    """collate -> KPFCNN -> descriptor + detector loss (-> backward -> optimizer) for pairs of a fixed size,
+    eagerly on static shapes or as one CUDA graph.
+
+    step = PairStep(model, config, limits, caps, n0, n1, loss_fn, optimizer, flat_grads)
+    step.capture()                      # optional: CUDA graph
+    loss = step(data)                   # data = (pts0, pts1, feat0, feat1, corr, dist_keypts): tensors on any device
+    step.check()                        # raises if a capacity / candidate buffer overflowed (host sync)
+    """
+
+    def __init__(self, model, config, limits, caps, n0, n1, loss_fn, optimizer=None, flat_grads=None,
+                 num_node=128, group=None, cross_fragment=None):
+        dev = next(model.parameters()).device
+        self.model, self.config, self.limits, self.caps = model, config, [int(v) for v in limits], list(caps)
+        self.loss_fn, self.optimizer, self.flat = loss_fn, optimizer, flat_grads
+        self.cross_fragment, self.group = cross_fragment, group
+        self.n0 = n0
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.inputs = (torch.zeros((n0, 3), **f32), torch.zeros((n1, 3), **f32), torch.ones((n0, 1), **f32),
+                       torch.ones((n1, 1), **f32), torch.zeros((num_node, 2), dtype=torch.int64, device=dev),
+                       torch.zeros((num_node, num_node), dtype=torch.float64, device=dev))
+        self.lengths0 = torch.tensor([n0, n1], dtype=torch.int32, device=dev)
+        self.graph = None
+        self.loss = torch.zeros((), **f32)
+        self.desc_loss = torch.zeros((), **f32)
+        self.det_loss = torch.zeros((), **f32)
+        self.status = None
+        self.batch = None
+
+    # -- the step on the static input buffers
+    def _body(self):
+        cfg = self.config
+        batch, status = collate_static(*self.inputs, cfg, self.limits, self.caps, self.lengths0)
+        feats, scores = self.model(batch)
+        c = batch['corr']
+        ia, ip = c[:, 0], c[:, 1] + self.n0
+        a, p = gather(feats, ia), gather(feats, ip)            # trainer.py:91-94
+        sa, sp = gather(scores, ia), gather(scores, ip)
+        if self.cross_fragment is not None:
+            out = self.cross_fragment(self.loss_fn, a, p, batch['dist_keypts'], sa, sp, self.group)
+        else:
+            out = self.loss_fn(a, p, batch['dist_keypts'], sa, sp)
+        loss = out['desc_loss'] * cfg.desc_loss_weight + out['det_loss'] * cfg.det_loss_weight
+        if self.optimizer is not None:
+            if self.flat is not None:
+                self.flat.zero()
+            else:
+                self.optimizer.zero_grad(set_to_none=False)
+            loss.backward()
+            if self.flat is not None:
+                self.flat.allreduce(self.group)
+            self.optimizer.step()
+        self.loss.copy_(loss.detach())
+        self.desc_loss.copy_(out['desc_loss'].detach())
+        self.det_loss.copy_(out['det_loss'].detach())
+        if self.status is None:
+            self.status = torch.zeros_like(status)
+        self.status.copy_(status)
+        self.batch = batch
+        return loss
+
+    def load(self, data):
+        for dst, src in zip(self.inputs, data):
+            if not isinstance(src, torch.Tensor):
+                src = torch.as_tensor(src)
+            dst.copy_(src, non_blocking=True)
+
+    def capture(self, warmup=3):
+        """Warm up on a side stream (lazy optimizer state, cudaFuncSetAttribute calls, allocator), then capture."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._body()
+        self.graph = g
+        return self
+
+    def __call__(self, data=None):
+        if data is not None:
+            self.load(data)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._body()
+        return self.loss
+
+    def check(self):
+        """Host-side validity check of the last step (one small D2H read)."""
+        if self.status is not None and bool(self.status.any()):
+            raise RuntimeError("PairStep: a static capacity or a neighbour candidate buffer overflowed "
+                               "(status=%s); re-plan the capacities or use the exact-shape pipeline"
+                               % self.status.tolist())

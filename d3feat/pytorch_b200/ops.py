@@ -69,8 +69,9 @@ def _pow2ceil(v):
 
 # --------------------------------------------------------------------------- radius neighbours
 def radius_neighbors_raw(queries, supports, q_len, s_len, radius, max_cols, index_dtype=torch.int64,
-                         row_capacity=None, count_only=False):
-    """One call of d3f_radius_neighbors.  Returns (idx [Nq,max_cols] or None, info int32[4] on device)."""
+                         row_capacity=None, count_only=False, pad_index=-1):
+    """One call of d3f_radius_neighbors (no host sync).  Returns (idx [Nq,max_cols] or None, info int32[4] on
+    device).  `queries` / `supports` may have more rows than sum(q_len) / sum(s_len) (static capacities)."""
     lib = _lib.load()
     queries, supports = _cuda_f32(queries, "queries"), _cuda_f32(supports, "supports")
     dev = queries.device
@@ -90,7 +91,7 @@ def radius_neighbors_raw(queries, supports, q_len, s_len, radius, max_cols, inde
     with _Timed(("radius_neighbors", nq, ns)):
       _lib.check(lib.d3f_radius_neighbors(_p(queries), _p(supports), _p(q_len), _p(s_len), nb, nq, ns,
                                         float(radius), int(max_cols) if not count_only else 0, _p(out),
-                                        1 if index_dtype == torch.int64 else 0, _p(info), int(row_capacity),
+                                        1 if index_dtype == torch.int64 else 0, int(pad_index), _p(info), int(row_capacity),
                                         _p(ws), ws.numel(), _stream()))
     return out, info
 
@@ -124,19 +125,30 @@ def grid_subsample(points, lengths, sample_dl):
     points = _cuda_f32(points, "points")
     dev = points.device
     lengths = lengths.to(device=dev, dtype=torch.int32).contiguous()
+    out, out_len = grid_subsample_raw(points, lengths, sample_dl, points.shape[0])
+    host_len = out_len.tolist()
+    if any(v < 0 for v in host_len[:-1]):
+        raise _lib.D3FError("grid_subsample: voxel grid exceeds the supported key range (code %s)" % host_len)
+    return out[:sum(host_len[:-1])], out_len[:-1]
+
+
+def grid_subsample_raw(points, lengths, sample_dl, out_capacity):
+    """One call of d3f_grid_subsample (no host sync) -> (out [out_capacity,3], out_len int32 [B+1] on device;
+    out_len[B] = 1 if out_capacity was too small, out_len[b] = -1 on an unsupported voxel grid)."""
+    lib = _lib.load()
+    points = _cuda_f32(points, "points")
+    dev = points.device
+    lengths = lengths.to(device=dev, dtype=torch.int32).contiguous()
     n, nb = points.shape[0], lengths.shape[0]
-    out = torch.empty((n, 3), dtype=torch.float32, device=dev)
-    out_len = torch.empty(nb, dtype=torch.int32, device=dev)
+    out = torch.empty((int(out_capacity), 3), dtype=torch.float32, device=dev)
+    out_len = torch.empty(nb + 1, dtype=torch.int32, device=dev)
     ws = _ws(lib.d3f_grid_subsample_workspace_bytes(n, nb), dev)
     global launch_count
     launch_count += 1
     with _Timed(("grid_subsample", n)):
-      _lib.check(lib.d3f_grid_subsample(_p(points), _p(lengths), nb, n, float(sample_dl), _p(out), _p(out_len),
-                                      _p(ws), ws.numel(), _stream()))
-    host_len = out_len.tolist()
-    if any(v < 0 for v in host_len):
-        raise _lib.D3FError("grid_subsample: voxel grid exceeds the supported key range (code %s)" % host_len)
-    return out[:sum(host_len)], out_len
+      _lib.check(lib.d3f_grid_subsample(_p(points), _p(lengths), nb, n, float(sample_dl), _p(out), int(out_capacity),
+                                      _p(out_len), _p(ws), ws.numel(), _stream()))
+    return out, out_len
 
 
 # --------------------------------------------------------------------------- KPConv

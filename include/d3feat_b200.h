@@ -59,6 +59,10 @@ unsigned long long d3f_launch_count(void);
  *
  *   queries   [n_queries,3] f32     supports [n_supports,3] f32
  *   q_lengths [n_batch] i32         s_lengths [n_batch] i32      (device)
+ *   n_queries / n_supports are the ALLOCATED row counts; the real rows are the first sum(q_lengths) /
+ *   sum(s_lengths) ones.  They may be smaller (static capacities for CUDA-graph capture): padding query
+ *   rows get an all-shadow row, padding support rows are never returned.
+ *   pad_index: the shadow index written into unused slots (-1: n_supports, the reference's value)
  *   out_idx   [n_queries,max_cols] i32 (idx_is_64=0) or i64 (idx_is_64=1); may be NULL: count only
  *   out_info  [4] i32 (device): [0] = max neighbour count over all queries BEFORE truncation
  *             (the reference's matrix width, neighbors.cpp:300), [1] = 1 if some row had more
@@ -70,7 +74,7 @@ size_t d3f_radius_neighbors_workspace_bytes(int n_queries, int n_supports, int n
 int d3f_radius_neighbors(const float* queries, const float* supports,
                          const int32_t* q_lengths, const int32_t* s_lengths, int n_batch,
                          int n_queries, int n_supports, float radius, int max_cols,
-                         void* out_idx, int idx_is_64, int32_t* out_info, int row_capacity,
+                         void* out_idx, int idx_is_64, int pad_index, int32_t* out_info, int row_capacity,
                          void* workspace, size_t workspace_bytes, d3f_stream stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -80,13 +84,14 @@ int d3f_radius_neighbors(const float* queries, const float* supports,
  * Output values AND order are bit-identical to the reference, i.e. the iteration order of
  * libstdc++'s std::unordered_map<size_t,SampledData> (grid_subsampling.cpp:48,85).
  *
- *   points [n_points,3] f32, lengths [n_batch] i32 (device)
- *   out_points  [n_points,3] f32 capacity; the first sum(out_lengths) rows are valid
- *   out_lengths [n_batch] i32 (device)
+ *   points [n_points,3] f32 (n_points = allocated rows, real rows = sum(lengths)), lengths [n_batch] i32 (device)
+ *   out_points  [out_capacity,3] f32; the first sum(out_lengths[0..n_batch)) rows are valid, the rest is zeroed
+ *   out_lengths [n_batch + 1] i32 (device): per-cloud counts (-1: voxel grid beyond the supported key range);
+ *               [n_batch] = 1 if out_capacity was too small (the output is then truncated)
  */
 size_t d3f_grid_subsample_workspace_bytes(int n_points, int n_batch);
 int d3f_grid_subsample(const float* points, const int32_t* lengths, int n_batch, int n_points,
-                       float sample_dl, float* out_points, int32_t* out_lengths,
+                       float sample_dl, float* out_points, int out_capacity, int32_t* out_lengths,
                        void* workspace, size_t workspace_bytes, d3f_stream stream);
 
 /* ------------------------------------------------------------------------------------------
