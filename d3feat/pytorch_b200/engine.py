@@ -168,6 +168,8 @@ class PairStep:
 
     def capture(self, warmup=3):
         """Warm up on a side stream (lazy optimizer state, cudaFuncSetAttribute calls, allocator), then capture."""
+        import gc
+        gc.collect()   # drop autograd graphs (and their AccumulateGrad nodes) left over from eager steps on other streams
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):

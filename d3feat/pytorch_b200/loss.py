@@ -28,8 +28,10 @@ class _PairLossFunction(torch.autograd.Function):
                                                                  kind, metric, safe_radius, pos_margin, neg_margin,
                                                                  log_scale)
         ctx.set_materialize_grads(False)
-        ctx.saved = saved
-        ctx.aux, ctx.dists_saved = aux, dists
+        anchor_c, positive_c, dk, sa, sp = saved
+        # `dists` is an output: it must go through save_for_backward (a plain ctx attribute would form a
+        # reference cycle ctx -> dists -> grad_fn that keeps the whole autograd graph alive until the GC runs)
+        ctx.save_for_backward(anchor_c, positive_c, dk, sa, sp, dists, aux)
         ctx.cfg = (kind, metric, safe_radius, pos_margin, neg_margin, log_scale)
         ctx.score_shapes = (None if anc_score is None else anc_score.shape,
                             None if pos_score is None else pos_score.shape)
@@ -42,11 +44,12 @@ class _PairLossFunction(torch.autograd.Function):
         if g_dists is not None:
             raise RuntimeError("the `dists` output of the fused pair loss only feeds DetLoss inside the kernel; "
                                "use PairLoss (or DetLoss on it) rather than differentiating it directly")
-        gl = torch.stack([g_desc if g_desc is not None else torch.zeros((), device=ctx.aux.device),
-                          g_det if g_det is not None else torch.zeros((), device=ctx.aux.device)]).float()
+        anchor_c, positive_c, dk, sa, sp, dists, aux = ctx.saved_tensors
+        gl = torch.stack([g_desc if g_desc is not None else torch.zeros((), device=aux.device),
+                          g_det if g_det is not None else torch.zeros((), device=aux.device)]).float()
         kind, metric, safe_radius, pm, nm, ls = ctx.cfg
-        ga, gp, gsa, gsp = ops.pair_loss_backward(ctx.saved, kind, metric, safe_radius, pm, nm, ls,
-                                                  ctx.dists_saved, ctx.aux, gl)
+        ga, gp, gsa, gsp = ops.pair_loss_backward((anchor_c, positive_c, dk, sa, sp), kind, metric, safe_radius, pm, nm, ls,
+                                                  dists, aux, gl)
         sa_shape, sp_shape = ctx.score_shapes
         gsa = gsa.reshape(sa_shape) if gsa is not None else None
         gsp = gsp.reshape(sp_shape) if gsp is not None else None
