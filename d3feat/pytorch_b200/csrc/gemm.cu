@@ -173,6 +173,24 @@ tc_gemm_kernel(D3fGemm g) {
     }
 
     // epilogue: rows m0+wm+mi*16+gq (+8), cols n0+wn+ni*8+2*tq (+1)
+    if (g.partial) {   // deterministic split-K: raw partial sums, reduced in split order by gemm_reduce_kernel
+        float* part = g.partial + (size_t)blockIdx.z * g.M * g.N;
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int m = m0 + wm + mi * 16 + gq + half * 8;
+                if (m >= g.M) continue;
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int n = n0 + wn + ni * 8 + 2 * tq + e;
+                        if (n < g.N) part[(size_t)m * g.N + n] = acc[mi][ni][half * 2 + e];
+                    }
+            }
+        return;
+    }
     const bool atomic = gridDim.z > 1;
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi)
@@ -197,24 +215,61 @@ tc_gemm_kernel(D3fGemm g) {
         }
 }
 
+__global__ void gemm_reduce_kernel(const float* __restrict__ part, int splits, int M, int N, float* __restrict__ C,
+                                   int ldc, const float* __restrict__ rs, const float* __restrict__ bias, int act,
+                                   float slope) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)M * N) return;
+    const int m = (int)(t / N), n = (int)(t % N);
+    float v = 0.f;
+    for (int z = 0; z < splits; ++z) v += part[(size_t)z * M * N + t];   // fixed order
+    if (rs) v *= rs[m];
+    if (bias) v += bias[n];
+    if (act) v = v > 0.f ? v : v * slope;
+    C[(size_t)m * ldc + n] = v;
+}
+
+// deterministic split: a function of K only (so the summation order of a row never depends on M)
+constexpr int DET_ROWS_MAX = 4096;   // above this many rows the output grid alone fills the chip: no split
+constexpr int DET_KPS = 256;
+inline int det_splits(int M, int K) { return (M <= DET_ROWS_MAX && K >= 2 * DET_KPS) ? d3f_ceil_div(K, DET_KPS) : 1; }
+
 }  // namespace
 
-int d3f_gemm_launch(const D3fGemm& in, bool ta, bool tb, cudaStream_t stream) {
+size_t d3f_gemm_det_workspace_bytes(int M, int N, int K) {
+    const int s = det_splits(M, K);
+    return s > 1 ? sizeof(float) * (size_t)s * M * N : 0;
+}
+
+int d3f_gemm_launch(const D3fGemm& in, bool ta, bool tb, cudaStream_t stream, float* det_ws, size_t det_ws_bytes) {
     D3fGemm g = in;
+    g.partial = nullptr;
     if (g.M <= 0 || g.N <= 0) return D3F_OK;
     const int tiles = d3f_ceil_div(g.M, BM) * d3f_ceil_div(g.N, BN);
-    int splits = 1;
-    const bool plain = !g.bias && !g.act;   // split-K partials are atomically added: no non-linear epilogue
-    if (g.K > 0 && plain && tiles < 148) {
-        splits = min(d3f_ceil_div(296, tiles), d3f_ceil_div(g.K, 4 * BK));
-        if (splits < 1) splits = 1;
+    int splits = 1, kps;
+    const bool plain = !g.bias && !g.act;   // atomically combined partials cannot take a non-linear epilogue
+    if (det_ws) {
+        splits = det_splits(g.M, g.K);
+        kps = splits > 1 ? DET_KPS : d3f_ceil_div(g.K > 0 ? g.K : 1, BK) * BK;
+        if (splits > 1) {
+            D3F_REQUIRE(det_ws_bytes >= sizeof(float) * (size_t)splits * g.M * g.N, D3F_ERR_WORKSPACE,
+                        "deterministic split-K workspace too small");
+            g.partial = det_ws;
+        }
+    } else {
+        if (g.K > 0 && plain && tiles < 148) {
+            splits = min(d3f_ceil_div(296, tiles), d3f_ceil_div(g.K, 4 * BK));
+            if (splits < 1) splits = 1;
+        }
+        kps = d3f_ceil_div(d3f_ceil_div(g.K > 0 ? g.K : 1, splits), BK) * BK;
+        splits = d3f_ceil_div(g.K > 0 ? g.K : 1, kps);
+        if (splits > 1) D3F_CHECK_CUDA(cudaMemsetAsync(g.C, 0, sizeof(float) * (size_t)g.M * g.ldc, stream));
     }
-    int kps = d3f_ceil_div(d3f_ceil_div(g.K > 0 ? g.K : 1, splits), BK) * BK;
-    splits = d3f_ceil_div(g.K > 0 ? g.K : 1, kps);
     g.k_per_split = kps;
-    if (splits > 1 || g.K == 0)
+    if (g.K == 0) {
         D3F_CHECK_CUDA(cudaMemsetAsync(g.C, 0, sizeof(float) * (size_t)g.M * g.ldc, stream));
-    if (g.K == 0) return D3F_OK;
+        return D3F_OK;
+    }
     const size_t smem = sizeof(float) * 2 * (A_STAGE + B_STAGE);
     dim3 grid(d3f_ceil_div(g.N, BN), d3f_ceil_div(g.M, BM), splits);
 #define LAUNCH(TA_, TB_)                                                                                   \
@@ -232,6 +287,12 @@ int d3f_gemm_launch(const D3fGemm& in, bool ta, bool tb, cudaStream_t stream) {
     else { d3f_set_error("gemm: TT mode is not used on the hot path"); return D3F_ERR_UNSUPPORTED; }
 #undef LAUNCH
     D3F_CHECK_LAUNCH();
+    if (g.partial) {
+        const size_t total = (size_t)g.M * g.N;
+        gemm_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(g.partial, splits, g.M, g.N, g.C, g.ldc,
+                                                                              g.rs, g.bias, g.act, g.slope);
+        D3F_CHECK_LAUNCH();
+    }
     return D3F_OK;
 }
 
@@ -243,6 +304,6 @@ extern "C" int d3f_gemm(int trans_a, int trans_b, int M, int N, int K, const flo
     if (M == 0 || N == 0) return D3F_OK;
     D3F_REQUIRE(C && (K == 0 || (A && B)), D3F_ERR_INVALID, "null pointer");
     D3F_REQUIRE(!(k_scale && trans_b), D3F_ERR_UNSUPPORTED, "k_scale is applied on B[k][n] loads only");
-    D3fGemm g{M, N, K, A, lda, B, ldb, C, ldc, row_scale, k_scale, bias, leaky_relu, slope, 0};
+    D3fGemm g{M, N, K, A, lda, B, ldb, C, ldc, row_scale, k_scale, bias, leaky_relu, slope, 0, nullptr};
     return d3f_gemm_launch(g, trans_a != 0, trans_b != 0, (cudaStream_t)stream);
 }

@@ -13,7 +13,14 @@ struct D3fGemm {
     int act;             // 1 = LeakyReLU(slope) after the bias
     float slope;
     int k_per_split;     // filled by the launcher
+    float* partial;      // filled by the launcher: deterministic split-K partials [splits][M][N], or null
 };
 
 // C[M,N] = act(rs[m] * sum_k opA(m,k) * ks[k] * opB(k,n) + bias[n]);  ta: A stored [K,M];  tb: B stored [N,K]
-int d3f_gemm_launch(const D3fGemm& g, bool ta, bool tb, cudaStream_t stream);
+// `det_ws` != null selects the DETERMINISTIC split-K used by the forward pass: the split size depends on K
+// only (never on M), partial tiles go to det_ws and are summed in split order by a second kernel, so a row of C
+// is bit-identical run to run and independent of how many (padding) rows M has.  Without it, split-K partials
+// are combined with float atomics (backward GEMMs: order-dependent at the 1e-7 level, like the scatter-adds).
+size_t d3f_gemm_det_workspace_bytes(int M, int N, int K);
+int d3f_gemm_launch(const D3fGemm& g, bool ta, bool tb, cudaStream_t stream, float* det_ws = nullptr,
+                    size_t det_ws_bytes = 0);

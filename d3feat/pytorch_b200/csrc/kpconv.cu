@@ -445,11 +445,16 @@ int kp_warps_per_cta(int H, bool with_rel, size_t* smem) {
     return warps;
 }
 
-struct KpWs { unsigned char* rowpos; float* dwf; };
-size_t kp_layout(KpWs* w, void* base, size_t cap, int nq, int ns, int K, int cin) {
+struct KpWs { unsigned char* rowpos; float* dwf; float* det; size_t det_bytes; };
+// dwf (backward) and the deterministic split-K partials (forward) share the same region
+size_t kp_layout(KpWs* w, void* base, size_t cap, int nq, int ns, int K, int cin, int cout) {
     WsCursor c{(char*)base, 0, cap};
     w->rowpos = c.take<unsigned char>((size_t)(ns > 0 ? ns : 1));
-    w->dwf = c.take<float>((size_t)(nq > 0 ? nq : 1) * K * cin);
+    const size_t dwf_floats = (size_t)(nq > 0 ? nq : 1) * K * cin;
+    w->det_bytes = d3f_gemm_det_workspace_bytes(nq, cout, K * cin);
+    const size_t floats = dwf_floats > w->det_bytes / sizeof(float) ? dwf_floats : w->det_bytes / sizeof(float);
+    w->dwf = c.take<float>(floats);
+    w->det = w->dwf;
     return c.off;
 }
 
@@ -500,9 +505,9 @@ int kp_set_smem(Kern kern, size_t smem) {
 
 extern "C" size_t d3f_kpconv_workspace_bytes(int n_queries, int n_supports, int n_neighbors, int K, int c_in,
                                              int c_out) {
-    (void)n_neighbors; (void)c_out;
+    (void)n_neighbors;
     KpWs w;
-    return kp_layout(&w, nullptr, 0, n_queries, n_supports, K, c_in);
+    return kp_layout(&w, nullptr, 0, n_queries, n_supports, K, c_in, c_out);
 }
 
 extern "C" int d3f_kpconv_forward(const float* q_pts, const float* s_pts, const void* inds, int idx_is_64,
@@ -520,7 +525,7 @@ extern "C" int d3f_kpconv_forward(const float* q_pts, const float* s_pts, const 
     D3F_REQUIRE(!modulations || wf_unmod, D3F_ERR_INVALID, "wf_unmod is required with modulations");
     D3F_REQUIRE(influence >= 0 && influence <= 2 && aggregation >= 0 && aggregation <= 1, D3F_ERR_INVALID, "bad mode");
     KpWs w;
-    const size_t need = kp_layout(&w, workspace, workspace_bytes, nq, ns, K, cin);
+    const size_t need = kp_layout(&w, workspace, workspace_bytes, nq, ns, K, cin, cout);
     D3F_REQUIRE(workspace && need <= workspace_bytes, D3F_ERR_WORKSPACE, "workspace too small");
     if (ns > 0) {
         kp_rowpos_kernel<<<d3f_ceil_div(ns, 8), 256, 0, stream>>>(x, ns, cin, w.rowpos);
@@ -533,8 +538,10 @@ extern "C" int d3f_kpconv_forward(const float* q_pts, const float* s_pts, const 
     const int grid = d3f_ceil_div(nq, warps);
     KP_DISPATCH_ALL(kp_correlate_kernel, a, wf, wf_unmod, inv_n, deformed ? min_d2 : nullptr);
     D3F_CHECK_LAUNCH();
-    D3fGemm g{nq, cout, K * cin, wf, K * cin, weights, cout, out, cout, inv_n, nullptr, nullptr, 0, 0.f, 0};
-    return d3f_gemm_launch(g, false, false, stream);
+    D3fGemm g{nq, cout, K * cin, wf, K * cin, weights, cout, out, cout, inv_n, nullptr, nullptr, 0, 0.f, 0, nullptr};
+    // forward: deterministic, padding-independent split-K (a 1e-7 perturbation here can flip a LeakyReLU mask)
+    float dummy;
+    return d3f_gemm_launch(g, false, false, stream, w.det_bytes ? w.det : &dummy, w.det_bytes);
 }
 
 extern "C" int d3f_kpconv_backward(const float* q_pts, const float* s_pts, const void* inds, int idx_is_64,
@@ -557,12 +564,12 @@ extern "C" int d3f_kpconv_backward(const float* q_pts, const float* s_pts, const
     D3F_REQUIRE(q_pts && s_pts && (inds || H == 0) && x && weights && kernel_points && wf && inv_n && grad_out,
                 D3F_ERR_INVALID, "null pointer");
     KpWs w;
-    const size_t need = kp_layout(&w, workspace, workspace_bytes, nq, ns, K, cin);
+    const size_t need = kp_layout(&w, workspace, workspace_bytes, nq, ns, K, cin, cout);
     D3F_REQUIRE(workspace && need <= workspace_bytes, D3F_ERR_WORKSPACE, "workspace too small");
     const int KC = K * cin;
     // dW[kc, o] = sum_i wf[i, kc] * inv_n[i] * g[i, o]
     if (grad_weights) {
-        D3fGemm g{KC, cout, nq, wf, KC, grad_out, cout, grad_weights, cout, nullptr, inv_n, nullptr, 0, 0.f, 0};
+        D3fGemm g{KC, cout, nq, wf, KC, grad_out, cout, grad_weights, cout, nullptr, inv_n, nullptr, 0, 0.f, 0, nullptr};
         rc = d3f_gemm_launch(g, true, false, stream);
         if (rc) return rc;
     }
@@ -570,7 +577,7 @@ extern "C" int d3f_kpconv_backward(const float* q_pts, const float* s_pts, const
     if (!need_scatter) return D3F_OK;
     // dwf[i, kc] = inv_n[i] * sum_o g[i, o] * W[kc, o]
     {
-        D3fGemm g{nq, KC, cout, grad_out, cout, weights, cout, w.dwf, KC, inv_n, nullptr, nullptr, 0, 0.f, 0};
+        D3fGemm g{nq, KC, cout, grad_out, cout, weights, cout, w.dwf, KC, inv_n, nullptr, nullptr, 0, 0.f, 0, nullptr};
         rc = d3f_gemm_launch(g, false, true, stream);
     }
     if (rc) return rc;

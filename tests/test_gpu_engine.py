@@ -62,9 +62,8 @@ def test_pair_step_matches_drop_in_pipeline(cuda, deform, graph):
     cfg, limits, model = _setup(cuda, deform)
     loss_fn = PairLoss("circle", "euclidean", 10, 0.1, 0.1, 1.4)
     pairs = [synthetic.fragment_pair(1500, seed=5 + i, num_node=64) for i in range(2)]
-    # reference: exact-shape drop-in pipeline, gradients of the second pair
-    grads = []
-    for data in pairs:
+    # reference: exact-shape drop-in pipeline, per-pair gradients
+    def drop_in(data):
         batch = collate_fn_descriptor([data], cfg, limits)
         feats, scores = model(batch)
         c = batch["corr"].long()
@@ -72,8 +71,9 @@ def test_pair_step_matches_drop_in_pipeline(cuda, deform, graph):
         o = loss_fn(gather(feats, ia), gather(feats, ip), batch["dist_keypts"], gather(scores, ia), gather(scores, ip))
         model.zero_grad(set_to_none=True)
         (o["desc_loss"] + o["det_loss"]).backward()
-        grads.append(({k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None},
-                      float(o["desc_loss"]), float(o["det_loss"])))
+        return ({k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None},
+                float(o["desc_loss"].detach()), float(o["det_loss"].detach()))
+    grads = [drop_in(d) for d in pairs]
     sizes = [[int(p.shape[0]) for p in collate_fn_descriptor([d], cfg, limits)["points"]] for d in pairs]
     caps = plan_capacities(sizes, margin=1.2, align=32)
 
