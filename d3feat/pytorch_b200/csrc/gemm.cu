@@ -13,6 +13,7 @@
 // prefetch of the next K tile + two shared-memory stages (one barrier per K tile).
 #include "common.cuh"
 #include "gemm.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -241,6 +242,19 @@ size_t d3f_gemm_det_workspace_bytes(int M, int N, int K) {
     return s > 1 ? sizeof(float) * (size_t)s * M * N : 0;
 }
 
+int d3f_gemm_tcgen05_launch(const D3fGemm& g, bool ta, bool tb, int splits, cudaStream_t stream);
+
+// 1 = tcgen05 / TMEM kernel (gemm_tcgen05.cu, default), 0 = legacy mma.sync kernel (this file)
+static int g_gemm_impl = -1;
+extern "C" void d3f_set_gemm_impl(int use_tcgen05) { g_gemm_impl = use_tcgen05 ? 1 : 0; }
+static int gemm_impl() {
+    if (g_gemm_impl < 0) {
+        const char* e = getenv("D3F_GEMM_IMPL");
+        g_gemm_impl = (e && e[0] == 'm') ? 0 : 1;
+    }
+    return g_gemm_impl;
+}
+
 int d3f_gemm_launch(const D3fGemm& in, bool ta, bool tb, cudaStream_t stream, float* det_ws, size_t det_ws_bytes) {
     D3fGemm g = in;
     g.partial = nullptr;
@@ -270,6 +284,10 @@ int d3f_gemm_launch(const D3fGemm& in, bool ta, bool tb, cudaStream_t stream, fl
         D3F_CHECK_CUDA(cudaMemsetAsync(g.C, 0, sizeof(float) * (size_t)g.M * g.ldc, stream));
         return D3F_OK;
     }
+    if (gemm_impl() == 1) {
+        int rc5 = d3f_gemm_tcgen05_launch(g, ta, tb, splits, stream);
+        if (rc5) return rc5;
+    } else {
     const size_t smem = sizeof(float) * 2 * (A_STAGE + B_STAGE);
     dim3 grid(d3f_ceil_div(g.N, BN), d3f_ceil_div(g.M, BM), splits);
 #define LAUNCH(TA_, TB_)                                                                                   \
@@ -287,6 +305,7 @@ int d3f_gemm_launch(const D3fGemm& in, bool ta, bool tb, cudaStream_t stream, fl
     else { d3f_set_error("gemm: TT mode is not used on the hot path"); return D3F_ERR_UNSUPPORTED; }
 #undef LAUNCH
     D3F_CHECK_LAUNCH();
+    }
     if (g.partial) {
         const size_t total = (size_t)g.M * g.N;
         gemm_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(g.partial, splits, g.M, g.N, g.C, g.ldc,

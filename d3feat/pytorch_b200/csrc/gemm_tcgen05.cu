@@ -1,0 +1,288 @@
+// 5th-generation tensor-core version of the fp32-accurate GEMM (see gemm.cu for the contract):
+// tcgen05.mma kind::tf32, 3xTF32 error compensation, accumulators in TMEM.
+//
+// One CTA (256 threads) computes a 128 x 64 tile.  Per 32-wide K tile all threads load A/B with coalesced
+// 128-bit global loads, split every value into tf32 hi + fp32 remainder lo, and store the four operand
+// tiles (A_hi, A_lo, B_hi, B_lo) into shared memory in the UMMA canonical NO-SWIZZLE layouts:
+//   K-major  (operand stored [rows][k]):  off(r,k) = (k/4)*LBO + (r/8)*128 + (r%8)*16 + (k%4)*4      SBO = 128 B
+//   MN-major (operand stored [k][rows]):  off(r,k) = (r/4)*SBO + (k/8)*LBO + (k%8)*16 + (r%4)*4
+// The free strides (LBO resp. SBO) are padded by 16 B, which makes the 128-bit shared stores of a quarter
+// warp hit 8 different bank groups.  One elected thread then issues 4 k-steps x 3 tcgen05.mma
+// (a_lo*b_hi, a_hi*b_lo, a_hi*b_hi) into a 128-lane x 64-column fp32 accumulator in tensor memory and
+// commits to an mbarrier; two shared-memory stages let the loads of tile t+1 overlap the MMAs of tile t.
+// Epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> row scale / bias / LeakyReLU -> global
+// (plain, atomic split-K, or deterministic split-K partials), exactly as the mma.sync kernel.
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 64, BK = 32, NT = 256;
+// K-major tiles: LBO = (rows/8)*128 + 16
+constexpr int A_LBO_K = (BM / 8) * 128 + 16;          // 2064
+constexpr int B_LBO_K = (BN / 8) * 128 + 16;          // 1040
+constexpr int A_BYTES_K = (BK / 4) * A_LBO_K;         // 16512
+constexpr int B_BYTES_K = (BK / 4) * B_LBO_K;         // 8320
+// MN-major tiles: SBO = 144, LBO = (rows/4)*144
+constexpr int SBO_M = 144;
+constexpr int A_LBO_M = (BM / 4) * SBO_M;             // 4608
+constexpr int B_LBO_M = (BN / 4) * SBO_M;             // 2304
+constexpr int A_BYTES_M = (BK / 8) * A_LBO_M;         // 18432
+constexpr int B_BYTES_M = (BK / 8) * B_LBO_M;         // 9216
+constexpr int A_TILE = 18432, B_TILE = 9216;          // max of both layouts, multiples of 16
+constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;  // hi + lo for A and B = 55296
+constexpr int SMEM_BYTES = 2 * STAGE_BYTES + 64;      // two stages + barriers / tmem pointer
+constexpr uint32_t TMEM_COLS = 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    // cute::UMMA::SmemDescriptor: start[0,14) | LBO[16,30) | SBO[32,46) | version=1 [46,48) | layout_type=0 (no swizzle)
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ULL << 46);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* fail) {
+    uint32_t done = 0;
+    for (long long spin = 0; spin < (1LL << 26); ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    if (fail) atomicExch(fail, 1);   // never hang the GPU: give up and flag the launch
+}
+
+__device__ __forceinline__ float tf32_hi(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+__device__ __forceinline__ float4 ld4g(const float* __restrict__ p, int valid, bool vec) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid >= 4 && vec) return __ldg((const float4*)p);
+    if (valid > 0) v.x = __ldg(p);
+    if (valid > 1) v.y = __ldg(p + 1);
+    if (valid > 2) v.z = __ldg(p + 2);
+    if (valid > 3) v.w = __ldg(p + 3);
+    return v;
+}
+
+__device__ __forceinline__ void st_split(char* hi, char* lo, uint32_t off, float4 v) {
+    float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    *(float4*)(hi + off) = h;
+    *(float4*)(lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+}
+
+__device__ int g_tc5_fail = 0;
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(NT)
+tc5_gemm_kernel(D3fGemm g) {
+    extern __shared__ __align__(128) char smem[];
+    uint64_t* bars = (uint64_t*)(smem + 2 * STAGE_BYTES);      // [0],[1]: stage free (MMA done);  [2]: all MMAs done
+    uint32_t* tmem_ptr = (uint32_t*)(smem + 2 * STAGE_BYTES + 32);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kbeg = blockIdx.z * g.k_per_split, kend = min(g.K, kbeg + g.k_per_split);
+    const int nk = (kend - kbeg + BK - 1) / BK;
+    const bool a_vec = (g.lda & 3) == 0 && (((size_t)g.A) & 15) == 0;
+    const bool b_vec = (g.ldb & 3) == 0 && (((size_t)g.B) & 15) == 0;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(tmem_ptr)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int i = 0; i < 3; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(&bars[i])), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem_d = *tmem_ptr;
+
+    // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6) | a,b = TF32 (2) [7,10),[10,13) | a_major [15] |
+    // b_major [16] | N>>3 [17,23) | M>>4 [24,29)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((TA ? 1u : 0u) << 15) | ((TB ? 0u : 1u) << 16) |
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+    float4 ra[4], rb[2];
+    auto load_tile = [&](int k0) {
+        if (!TA) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int m = m0 + (tid >> 3) + 32 * r, k = k0 + (tid & 7) * 4;
+                ra[r] = (m < g.M) ? ld4g(g.A + (size_t)m * g.lda + k, kend - k, a_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int k = k0 + (tid >> 5) + 8 * r, m = m0 + (tid & 31) * 4;
+                ra[r] = (k < kend) ? ld4g(g.A + (size_t)k * g.lda + m, g.M - m, a_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        if (TB) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int n = n0 + (tid >> 3) + 32 * r, k = k0 + (tid & 7) * 4;
+                rb[r] = (n < g.N) ? ld4g(g.B + (size_t)n * g.ldb + k, kend - k, b_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int k = k0 + (tid >> 4) + 16 * r, n = n0 + (tid & 15) * 4;
+                float4 v = (k < kend) ? ld4g(g.B + (size_t)k * g.ldb + n, g.N - n, b_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g.ks && k < kend) { const float s = g.ks[k]; v.x *= s; v.y *= s; v.z *= s; v.w *= s; }
+                rb[r] = v;
+            }
+        }
+    };
+    auto store_tile = [&](int stage) {
+        char* a_hi = smem + stage * STAGE_BYTES;
+        char* a_lo = a_hi + A_TILE;
+        char* b_hi = a_lo + A_TILE;
+        char* b_lo = b_hi + B_TILE;
+        if (!TA) {      // K-major: thread has (row, k4) -> one 16-byte unit
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int m = (tid >> 3) + 32 * r, k4 = tid & 7;
+                st_split(a_hi, a_lo, k4 * A_LBO_K + (m >> 3) * 128 + (m & 7) * 16, ra[r]);
+            }
+        } else {        // MN-major: thread has (k, m4) -> one 16-byte unit
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int k = (tid >> 5) + 8 * r, m4 = tid & 31;
+                st_split(a_hi, a_lo, m4 * SBO_M + (k >> 3) * A_LBO_M + (k & 7) * 16, ra[r]);
+            }
+        }
+        if (TB) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int n = (tid >> 3) + 32 * r, k4 = tid & 7;
+                st_split(b_hi, b_lo, k4 * B_LBO_K + (n >> 3) * 128 + (n & 7) * 16, rb[r]);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int k = (tid >> 4) + 16 * r, n4 = tid & 15;
+                st_split(b_hi, b_lo, n4 * SBO_M + (k >> 3) * B_LBO_M + (k & 7) * 16, rb[r]);
+            }
+        }
+    };
+
+    if (nk > 0) load_tile(kbeg);
+    for (int kt = 0; kt < nk; ++kt) {
+        const int stage = kt & 1;
+        if (kt >= 2) mbar_wait(smem_u32(&bars[stage]), ((kt >> 1) - 1) & 1, &g_tc5_fail);   // MMAs of tile kt-2 released this stage
+        store_tile(stage);
+        if (kt + 1 < nk) load_tile(kbeg + (kt + 1) * BK);                                     // global loads overlap the MMAs
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");                         // generic-proxy stores -> async proxy (UMMA)
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const uint32_t a_hi = smem_u32(smem + stage * STAGE_BYTES), a_lo = a_hi + A_TILE;
+            const uint32_t b_hi = a_lo + A_TILE, b_lo = b_hi + B_TILE;
+#pragma unroll
+            for (int ks = 0; ks < BK / 8; ++ks) {
+                // one MMA = 8 k values: two 16-byte k-units (K-major) or one 8-row k-group (MN-major)
+                const uint32_t ao = TA ? ks * A_LBO_M : ks * 2 * A_LBO_K;
+                const uint32_t bo = TB ? ks * 2 * B_LBO_K : ks * B_LBO_M;
+                const uint64_t dah = TA ? make_desc(a_hi + ao, A_LBO_M, SBO_M) : make_desc(a_hi + ao, A_LBO_K, 128);
+                const uint64_t dal = TA ? make_desc(a_lo + ao, A_LBO_M, SBO_M) : make_desc(a_lo + ao, A_LBO_K, 128);
+                const uint64_t dbh = TB ? make_desc(b_hi + bo, B_LBO_K, 128) : make_desc(b_hi + bo, B_LBO_M, SBO_M);
+                const uint64_t dbl = TB ? make_desc(b_lo + bo, B_LBO_K, 128) : make_desc(b_lo + bo, B_LBO_M, SBO_M);
+                mma_tf32(tmem_d, dal, dbh, idesc, (kt | ks) ? 1u : 0u);
+                mma_tf32(tmem_d, dah, dbl, idesc, 1u);
+                mma_tf32(tmem_d, dah, dbh, idesc, 1u);
+            }
+            // tcgen05.commit: arrive on the barrier when every MMA issued so far has completed
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+                         :: "r"(smem_u32(&bars[stage])) : "memory");
+            if (kt == nk - 1)
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+                             :: "r"(smem_u32(&bars[2])) : "memory");
+        }
+    }
+
+    // ---- epilogue: warp w reads TMEM lanes 32*(w%4) .. +31 (its row quarter), columns 32*(w/4) .. +31
+    if (nk > 0) mbar_wait(smem_u32(&bars[2]), 0, &g_tc5_fail);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const int row = m0 + (warp & 3) * 32 + lane;
+    const int col0 = (warp >> 2) * 32;
+    const bool atomic = gridDim.z > 1 && !g.partial;
+    const float sc = (row < g.M && g.rs) ? g.rs[row] : 1.0f;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t v[16];
+        const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(col0 + half * 16);
+        if (nk > 0) {
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                         : "r"(taddr) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = 0u;
+        }
+        if (row < g.M) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const int n = n0 + col0 + half * 16 + e;
+                if (n >= g.N) continue;
+                float x = __uint_as_float(v[e]);
+                if (g.partial) { g.partial[(size_t)blockIdx.z * g.M * g.N + (size_t)row * g.N + n] = x; continue; }
+                x *= sc;
+                float* dst = g.C + (size_t)row * g.ldc + n;
+                if (atomic) { atomicAdd(dst, x); continue; }
+                if (g.bias) x += g.bias[n];
+                if (g.act) x = x > 0.f ? x : x * g.slope;
+                *dst = x;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_d), "r"(TMEM_COLS) : "memory");
+}
+
+}  // namespace
+
+// launched by d3f_gemm_launch (gemm.cu) with the split decision already made
+int d3f_gemm_tcgen05_launch(const D3fGemm& g, bool ta, bool tb, int splits, cudaStream_t stream) {
+    dim3 grid(d3f_ceil_div(g.N, BN), d3f_ceil_div(g.M, BM), splits);
+#define LAUNCH5(TA_, TB_)                                                                                  \
+    do {                                                                                                   \
+        static bool attr_set = false;                                                                      \
+        if (!attr_set) {                                                                                   \
+            D3F_CHECK_CUDA(cudaFuncSetAttribute(tc5_gemm_kernel<TA_, TB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
+            attr_set = true;                                                                               \
+        }                                                                                                  \
+        tc5_gemm_kernel<TA_, TB_><<<grid, NT, SMEM_BYTES, stream>>>(g);                                    \
+    } while (0)
+    if (ta && !tb) LAUNCH5(true, false);
+    else if (!ta && tb) LAUNCH5(false, true);
+    else if (!ta && !tb) LAUNCH5(false, false);
+    else { d3f_set_error("gemm: TT mode is not used on the hot path"); return D3F_ERR_UNSUPPORTED; }
+#undef LAUNCH5
+    D3F_CHECK_LAUNCH();
+    return D3F_OK;
+}
+
+// 1 if any tcgen05 GEMM gave up waiting on an mbarrier (diagnostic; reads a device symbol -> synchronises)
+extern "C" int d3f_gemm_tcgen05_failed(void) {
+    int v = 0;
+    if (cudaMemcpyFromSymbol(&v, g_tc5_fail, sizeof(int)) != cudaSuccess) return -1;
+    return v;
+}

@@ -203,6 +203,10 @@ int d3f_detection_scores_backward(const float* features, const void* neighbors, 
  *   trans_a: A stored [K,M] else [M,K];  trans_b: B stored [N,K] else [K,N]  (row-major, lda/ldb/ldc in elements)
  *   row_scale / k_scale / bias may be NULL; k_scale needs trans_b == 0; leaky_relu != 0 applies max(v, slope*v).
  */
+/* GEMM back end: 1 = tcgen05.mma + TMEM (default), 0 = legacy mma.sync; d3f_gemm_tcgen05_failed() returns 1 if a
+ * tcgen05 kernel ever gave up waiting on its mbarrier (diagnostic, synchronises the device). */
+void d3f_set_gemm_impl(int use_tcgen05);
+int d3f_gemm_tcgen05_failed(void);
 int d3f_gemm(int trans_a, int trans_b, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
              float* C, int ldc, const float* row_scale, const float* k_scale, const float* bias,
              int leaky_relu, float slope, d3f_stream stream);

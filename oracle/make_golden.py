@@ -160,12 +160,40 @@ def golden_model(rblocks, rarch, rloss, rdata):
     for name, kw, n in [("kpfcnn_rigid", {}, 1500),
                         ("kpfcnn_deform", dict(architecture=build_architecture(5, deformable_from=3)), 1500)]:
         cfg = small_config(**kw)
-        data = synthetic.fragment_pair(n, seed=5, num_node=64)
         limits = [40, 40, 40, 40, 40] if "deform" not in name else [40, 40, 40, 120, 120]
-        batch = rdata.collate_fn_descriptor([data], cfg, limits)
         torch.manual_seed(0); np.random.seed(0)
         with contextlib.redirect_stdout(io.StringIO()):
             model = rarch.KPFCNN(cfg)
+        # Pick a data seed whose gradients are not on a LeakyReLU / arg-max knife edge: a pre-activation within
+        # fp32 rounding of zero makes the reference's own gradients depend on summation order (checked by
+        # re-running the reference in fp64: the fp32 and fp64 gradient norms must agree).
+        import copy
+        sd_probe = _inputs.kpfcnn_state_dict(cfg, seed=3)
+        circle_p = rloss.CircleLoss(dist_type="euclidean", log_scale=10, safe_radius=0.1, pos_margin=0.1, neg_margin=1.4)
+        for data_seed in range(5, 40):
+            data = synthetic.fragment_pair(n, seed=data_seed, num_node=64)
+            batch = rdata.collate_fn_descriptor([data], cfg, limits)
+            norms = []
+            gen = torch.Generator().manual_seed(1234)
+            for trial, dt in enumerate((torch.float32, torch.float64, torch.float32, torch.float32)):
+                m = copy.deepcopy(model)
+                m.load_state_dict(sd_probe, strict=True)
+                m = m.to(dt); m.train()
+                b = {k: ([t.to(dt) if t.is_floating_point() else t for t in v] if isinstance(v, list) else
+                         (v.to(dt) if v.is_floating_point() else v)) for k, v in batch.items()}
+                if trial >= 2:   # 2e-6 relative noise on the input features: above any kernel's rounding noise
+                    b["features"] = b["features"] * (1 + 2e-6 * torch.randn(b["features"].shape, generator=gen))
+                f_, s_ = m(b)
+                c_ = b["corr"].long(); n0_ = int(b["stack_lengths"][0][0])
+                dl_, _, _, _, _, dd_ = circle_p(f_[c_[:, 0]], f_[c_[:, 1] + n0_], b["dist_keypts"])
+                (dl_ + rloss.DetLoss()(dd_, s_[c_[:, 0]], s_[c_[:, 1] + n0_])).backward()
+                norms.append({k: float(p.grad.norm()) for k, p in m.named_parameters() if p.grad is not None})
+            worst = max(abs(norms[t_][k] - norms[1][k]) / max(norms[1][k], 1e-12) for k in norms[0] for t_ in (0, 2, 3))
+            print("  %s: data seed %d  reference grad-norm stability (fp32 / fp64 / 2 perturbed runs) %.1e" % (name, data_seed, worst))
+            if worst < 2.5e-5:
+                break
+        else:
+            raise RuntimeError("no knife-edge-free data seed found")
         shapes, kpr = _inputs.kpfcnn_shapes(cfg)
         ref_sd = model.state_dict()
         assert set(ref_sd) == set(shapes) | set(kpr), set(ref_sd) ^ (set(shapes) | set(kpr))
@@ -203,7 +231,7 @@ def golden_model(rblocks, rarch, rloss, rdata):
             _, s_eval2 = model_ref.kpfcnn_forward(sd, batch, cfg, training=False)
         assert rel(s_eval2, scores_eval) < 1e-5
         keys = sorted(gnorm)
-        save(name, features=feats.detach().numpy(), scores=scores.detach().numpy(),
+        save(name, data_seed=np.int64(data_seed), features=feats.detach().numpy(), scores=scores.detach().numpy(),
              scores_eval=scores_eval.numpy(), desc_loss=dl.detach().numpy(), det_loss=det.detach().numpy(),
              acc=np.float32(acc), grad_keys=np.array(keys), grad_norms=np.array([gnorm[k] for k in keys]),
              N=np.array([p.shape[0] for p in batch["points"]]),

@@ -8,10 +8,21 @@ from _util import rel_err
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["tcgen05", "mma"])
+def gemm_impl(request, cuda):
+    from d3feat.pytorch_b200 import _lib
+    lib = _lib.load()
+    lib.d3f_set_gemm_impl(1 if request.param == "tcgen05" else 0)
+    yield request.param
+    if request.param == "tcgen05":
+        assert lib.d3f_gemm_tcgen05_failed() == 0, "a tcgen05 GEMM gave up waiting on its mbarrier"
+    lib.d3f_set_gemm_impl(1)
+
+
 @pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False)])
 @pytest.mark.parametrize("M,N,K", [(1, 1, 1), (127, 65, 33), (128, 64, 32), (300, 45, 15), (1000, 512, 960),
                                    (190, 512, 7680), (480, 32, 40000), (4097, 33, 130)])
-def test_gemm_matches_fp64(cuda, ta, tb, M, N, K):
+def test_gemm_matches_fp64(cuda, gemm_impl, ta, tb, M, N, K):
     from d3feat.pytorch_b200 import ops
     rng = np.random.default_rng(M * 7 + N * 3 + K)
     A = rng.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
@@ -27,7 +38,7 @@ def test_gemm_matches_fp64(cuda, ta, tb, M, N, K):
     assert rel_err(got.cpu(), ref) < 2e-6 * max(1.0, np.sqrt(K) / 8), (M, N, K)
 
 
-def test_gemm_handles_strided_rows_and_bias_activation(cuda):
+def test_gemm_handles_strided_rows_and_bias_activation(cuda, gemm_impl):
     from d3feat.pytorch_b200 import ops
     rng = np.random.default_rng(3)
     X = torch.from_numpy(rng.standard_normal((500, 70)).astype(np.float32)).to(cuda)
@@ -38,7 +49,7 @@ def test_gemm_handles_strided_rows_and_bias_activation(cuda):
     assert rel_err(got.cpu(), ref.cpu()) < 2e-6
 
 
-def test_fused_linear_autograd(cuda):
+def test_fused_linear_autograd(cuda, gemm_impl):
     from d3feat.pytorch_b200 import ops
     rng = np.random.default_rng(4)
     x = torch.from_numpy(rng.standard_normal((777, 96)).astype(np.float32))
