@@ -3,13 +3,15 @@
 //
 // One CTA (256 threads) computes a 128 x 64 tile.  Per 32-wide K tile all threads load A/B with coalesced
 // 128-bit global loads, split every value into tf32 hi + fp32 remainder lo, and store the four operand
-// tiles (A_hi, A_lo, B_hi, B_lo) into shared memory in the UMMA canonical NO-SWIZZLE layouts:
-//   K-major  (operand stored [rows][k]):  off(r,k) = (k/4)*LBO + (r/8)*128 + (r%8)*16 + (k%4)*4      SBO = 128 B
-//   MN-major (operand stored [k][rows]):  off(r,k) = (r/4)*SBO + (k/8)*LBO + (k%8)*16 + (r%4)*4
-// The free strides (LBO resp. SBO) are padded by 16 B, which makes the 128-bit shared stores of a quarter
-// warp hit 8 different bank groups.  One elected thread then issues 4 k-steps x 3 tcgen05.mma
-// (a_lo*b_hi, a_hi*b_lo, a_hi*b_hi) into a 128-lane x 64-column fp32 accumulator in tensor memory and
-// commits to an mbarrier; two shared-memory stages let the loads of tile t+1 overlap the MMAs of tile t.
+// tiles (A_hi, A_lo, B_hi, B_lo) into shared memory in the UMMA canonical K-MAJOR NO-SWIZZLE layout
+//     off(r,k) = (k/4)*LBO + (r/8)*SBO + (r%8)*16 + (k%4)*4          (16-byte unit = 4 consecutive k of one row)
+// Operands that are stored transposed in global memory ([k][rows]: the TN / NN modes) are transposed in
+// registers (4x4) on the way in: for tf32 the only MN-major shared-memory layout the tensor core accepts is the
+// special 128B_BASE32B swizzle (cutlass sm100_common.inl), so everything is fed K-major instead.
+// SBO = 144 and LBO = (rows/8)*144 + 16 are padded so that every quarter-warp's 128-bit shared stores -- plain and
+// transposed -- land in 8 different bank groups.  One elected thread then issues 4 k-steps x 3 tcgen05.mma
+// (a_lo*b_hi, a_hi*b_lo, a_hi*b_hi) into a 128-lane x 64-column fp32 accumulator in tensor memory and commits
+// to an mbarrier; two shared-memory stages let the loads of tile t+1 overlap the MMAs of tile t.
 // Epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> row scale / bias / LeakyReLU -> global
 // (plain, atomic split-K, or deterministic split-K partials), exactly as the mma.sync kernel.
 #include "common.cuh"
@@ -18,19 +20,12 @@
 namespace {
 
 constexpr int BM = 128, BN = 64, BK = 32, NT = 256;
-// K-major tiles: LBO = (rows/8)*128 + 16
-constexpr int A_LBO_K = (BM / 8) * 128 + 16;          // 2064
-constexpr int B_LBO_K = (BN / 8) * 128 + 16;          // 1040
-constexpr int A_BYTES_K = (BK / 4) * A_LBO_K;         // 16512
-constexpr int B_BYTES_K = (BK / 4) * B_LBO_K;         // 8320
-// MN-major tiles: SBO = 144, LBO = (rows/4)*144
-constexpr int SBO_M = 144;
-constexpr int A_LBO_M = (BM / 4) * SBO_M;             // 4608
-constexpr int B_LBO_M = (BN / 4) * SBO_M;             // 2304
-constexpr int A_BYTES_M = (BK / 8) * A_LBO_M;         // 18432
-constexpr int B_BYTES_M = (BK / 8) * B_LBO_M;         // 9216
-constexpr int A_TILE = 18432, B_TILE = 9216;          // max of both layouts, multiples of 16
-constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;  // hi + lo for A and B = 55296
+constexpr int SBO = 144;                              // stride between 8-row groups (128 + 16 pad)
+constexpr int A_LBO = (BM / 8) * SBO + 16;            // stride between 16-byte k units: 2320
+constexpr int B_LBO = (BN / 8) * SBO + 16;            // 1168
+constexpr int A_TILE = (BK / 4) * A_LBO;              // 18560
+constexpr int B_TILE = (BK / 4) * B_LBO;              // 9344
+constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;  // hi + lo for A and B = 55808
 constexpr int SMEM_BYTES = 2 * STAGE_BYTES + 64;      // two stages + barriers / tmem pointer
 constexpr uint32_t TMEM_COLS = 64;
 
@@ -112,37 +107,37 @@ tc5_gemm_kernel(D3fGemm g) {
 
     // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6) | a,b = TF32 (2) [7,10),[10,13) | a_major [15] |
     // b_major [16] | N>>3 [17,23) | M>>4 [24,29)
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((TA ? 1u : 0u) << 15) | ((TB ? 0u : 1u) << 16) |
-                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    // (both operands are fed K-major: a_major = b_major = 0)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-    float4 ra[4], rb[2];
+    float4 ra[4], rb[4];
     auto load_tile = [&](int k0) {
-        if (!TA) {
+        if (!TA) {      // A[m][k]: thread = (row, 16-byte k unit)
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const int m = m0 + (tid >> 3) + 32 * r, k = k0 + (tid & 7) * 4;
                 ra[r] = (m < g.M) ? ld4g(g.A + (size_t)m * g.lda + k, kend - k, a_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-        } else {
+        } else {        // A[k][m]: thread = (4 k rows, 4 consecutive m), transposed in registers at store time
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int k = k0 + (tid >> 5) + 8 * r, m = m0 + (tid & 31) * 4;
-                ra[r] = (k < kend) ? ld4g(g.A + (size_t)k * g.lda + m, g.M - m, a_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < 4; ++j) {
+                const int k = k0 + (tid >> 5) * 4 + j, m = m0 + (tid & 31) * 4;
+                ra[j] = (k < kend) ? ld4g(g.A + (size_t)k * g.lda + m, g.M - m, a_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-        if (TB) {
+        if (TB) {       // B[n][k]
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const int n = n0 + (tid >> 3) + 32 * r, k = k0 + (tid & 7) * 4;
                 rb[r] = (n < g.N) ? ld4g(g.B + (size_t)n * g.ldb + k, kend - k, b_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-        } else {
+        } else if (tid < 128) {   // B[k][n]: thread = (4 k rows, 4 consecutive n)
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int k = k0 + (tid >> 4) + 16 * r, n = n0 + (tid & 15) * 4;
+            for (int j = 0; j < 4; ++j) {
+                const int k = k0 + (tid >> 4) * 4 + j, n = n0 + (tid & 15) * 4;
                 float4 v = (k < kend) ? ld4g(g.B + (size_t)k * g.ldb + n, g.N - n, b_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (g.ks && k < kend) { const float s = g.ks[k]; v.x *= s; v.y *= s; v.z *= s; v.w *= s; }
-                rb[r] = v;
+                if (g.ks && k < kend) { const float sc = g.ks[k]; v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc; }
+                rb[j] = v;
             }
         }
     };
@@ -151,30 +146,36 @@ tc5_gemm_kernel(D3fGemm g) {
         char* a_lo = a_hi + A_TILE;
         char* b_hi = a_lo + A_TILE;
         char* b_lo = b_hi + B_TILE;
-        if (!TA) {      // K-major: thread has (row, k4) -> one 16-byte unit
+        if (!TA) {
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const int m = (tid >> 3) + 32 * r, k4 = tid & 7;
-                st_split(a_hi, a_lo, k4 * A_LBO_K + (m >> 3) * 128 + (m & 7) * 16, ra[r]);
+                st_split(a_hi, a_lo, k4 * A_LBO + (m >> 3) * SBO + (m & 7) * 16, ra[r]);
             }
-        } else {        // MN-major: thread has (k, m4) -> one 16-byte unit
+        } else {
+            const int k4 = tid >> 5, mb = (tid & 31) * 4;
+            const float t[4][4] = {{ra[0].x, ra[1].x, ra[2].x, ra[3].x}, {ra[0].y, ra[1].y, ra[2].y, ra[3].y},
+                                   {ra[0].z, ra[1].z, ra[2].z, ra[3].z}, {ra[0].w, ra[1].w, ra[2].w, ra[3].w}};
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int k = (tid >> 5) + 8 * r, m4 = tid & 31;
-                st_split(a_hi, a_lo, m4 * SBO_M + (k >> 3) * A_LBO_M + (k & 7) * 16, ra[r]);
+            for (int e = 0; e < 4; ++e) {
+                const int m = mb + e;
+                st_split(a_hi, a_lo, k4 * A_LBO + (m >> 3) * SBO + (m & 7) * 16, make_float4(t[e][0], t[e][1], t[e][2], t[e][3]));
             }
         }
         if (TB) {
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const int n = (tid >> 3) + 32 * r, k4 = tid & 7;
-                st_split(b_hi, b_lo, k4 * B_LBO_K + (n >> 3) * 128 + (n & 7) * 16, rb[r]);
+                st_split(b_hi, b_lo, k4 * B_LBO + (n >> 3) * SBO + (n & 7) * 16, rb[r]);
             }
-        } else {
+        } else if (tid < 128) {
+            const int k4 = tid >> 4, nb = (tid & 15) * 4;
+            const float t[4][4] = {{rb[0].x, rb[1].x, rb[2].x, rb[3].x}, {rb[0].y, rb[1].y, rb[2].y, rb[3].y},
+                                   {rb[0].z, rb[1].z, rb[2].z, rb[3].z}, {rb[0].w, rb[1].w, rb[2].w, rb[3].w}};
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int k = (tid >> 4) + 16 * r, n4 = tid & 15;
-                st_split(b_hi, b_lo, n4 * SBO_M + (k >> 3) * B_LBO_M + (k & 7) * 16, rb[r]);
+            for (int e = 0; e < 4; ++e) {
+                const int n = nb + e;
+                st_split(b_hi, b_lo, k4 * B_LBO + (n >> 3) * SBO + (n & 7) * 16, make_float4(t[e][0], t[e][1], t[e][2], t[e][3]));
             }
         }
     };
@@ -194,13 +195,10 @@ tc5_gemm_kernel(D3fGemm g) {
             const uint32_t b_hi = a_lo + A_TILE, b_lo = b_hi + B_TILE;
 #pragma unroll
             for (int ks = 0; ks < BK / 8; ++ks) {
-                // one MMA = 8 k values: two 16-byte k-units (K-major) or one 8-row k-group (MN-major)
-                const uint32_t ao = TA ? ks * A_LBO_M : ks * 2 * A_LBO_K;
-                const uint32_t bo = TB ? ks * 2 * B_LBO_K : ks * B_LBO_M;
-                const uint64_t dah = TA ? make_desc(a_hi + ao, A_LBO_M, SBO_M) : make_desc(a_hi + ao, A_LBO_K, 128);
-                const uint64_t dal = TA ? make_desc(a_lo + ao, A_LBO_M, SBO_M) : make_desc(a_lo + ao, A_LBO_K, 128);
-                const uint64_t dbh = TB ? make_desc(b_hi + bo, B_LBO_K, 128) : make_desc(b_hi + bo, B_LBO_M, SBO_M);
-                const uint64_t dbl = TB ? make_desc(b_lo + bo, B_LBO_K, 128) : make_desc(b_lo + bo, B_LBO_M, SBO_M);
+                // one MMA = 8 k values = two 16-byte k units
+                const uint32_t ao = ks * 2 * A_LBO, bo = ks * 2 * B_LBO;
+                const uint64_t dah = make_desc(a_hi + ao, A_LBO, SBO), dal = make_desc(a_lo + ao, A_LBO, SBO);
+                const uint64_t dbh = make_desc(b_hi + bo, B_LBO, SBO), dbl = make_desc(b_lo + bo, B_LBO, SBO);
                 mma_tf32(tmem_d, dal, dbh, idesc, (kt | ks) ? 1u : 0u);
                 mma_tf32(tmem_d, dah, dbl, idesc, 1u);
                 mma_tf32(tmem_d, dah, dbh, idesc, 1u);
