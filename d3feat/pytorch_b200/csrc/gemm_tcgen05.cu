@@ -215,38 +215,63 @@ tc5_gemm_kernel(D3fGemm g) {
     // ---- epilogue: warp w reads TMEM lanes 32*(w%4) .. +31 (its row quarter), columns 32*(w/4) .. +31
     if (nk > 0) mbar_wait(smem_u32(&bars[2]), 0, &g_tc5_fail);
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    const int row = m0 + (warp & 3) * 32 + lane;
-    const int col0 = (warp >> 2) * 32;
-    const bool atomic = gridDim.z > 1 && !g.partial;
-    const float sc = (row < g.M && g.rs) ? g.rs[row] : 1.0f;
+    // TMEM -> registers (one row per thread) -> shared C tile [128][BN+4] (row stride = 4 banks mod 32: the
+    // 128-bit stores of a quarter warp are conflict-free) -> 128-bit row-contiguous global stores.
+    constexpr int LDC_S = BN + 4;
+    float* cs = (float*)smem;                       // the operand stages are free once bars[2] has completed
+    {
+        const int r_loc = (warp & 3) * 32 + lane, col0 = (warp >> 2) * 32;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        uint32_t v[16];
-        const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(col0 + half * 16);
-        if (nk > 0) {
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                         : "r"(taddr) : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-        } else {
+        for (int half = 0; half < 2; ++half) {
+            uint32_t v[16];
+            const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(col0 + half * 16);
+            if (nk > 0) {
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                             : "r"(taddr) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            } else {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = 0u;
-        }
-        if (row < g.M) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const int n = n0 + col0 + half * 16 + e;
-                if (n >= g.N) continue;
-                float x = __uint_as_float(v[e]);
-                if (g.partial) { g.partial[(size_t)blockIdx.z * g.M * g.N + (size_t)row * g.N + n] = x; continue; }
-                x *= sc;
-                float* dst = g.C + (size_t)row * g.ldc + n;
-                if (atomic) { atomicAdd(dst, x); continue; }
-                if (g.bias) x += g.bias[n];
-                if (g.act) x = x > 0.f ? x : x * g.slope;
-                *dst = x;
+                for (int e = 0; e < 16; ++e) v[e] = 0u;
             }
+#pragma unroll
+            for (int e = 0; e < 16; e += 4)
+                *(uint4*)&cs[r_loc * LDC_S + col0 + half * 16 + e] = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+        }
+    }
+    __syncthreads();
+    {
+        const bool atomic = gridDim.z > 1 && !g.partial;
+        const int c4 = (tid & 15) * 4, n = n0 + c4;
+        const bool vec_ok = g.partial ? ((g.N & 3) == 0) : ((g.ldc & 3) == 0 && (((size_t)g.C) & 15) == 0);
+#pragma unroll
+        for (int it = 0; it < BM / 16; ++it) {
+            const int r_loc = (tid >> 4) + 16 * it, row = m0 + r_loc;
+            if (row >= g.M || n >= g.N) continue;
+            float4 x = *(const float4*)&cs[r_loc * LDC_S + c4];
+            float xs[4] = {x.x, x.y, x.z, x.w};
+            if (g.partial) {
+                float* dst = g.partial + (size_t)blockIdx.z * g.M * g.N + (size_t)row * g.N + n;
+                if (vec_ok && n + 3 < g.N) *(float4*)dst = x;
+                else for (int e = 0; e < 4; ++e) if (n + e < g.N) dst[e] = xs[e];
+                continue;
+            }
+            const float sc = g.rs ? g.rs[row] : 1.0f;
+            float* dst = g.C + (size_t)row * g.ldc + n;
+            if (atomic) {
+                for (int e = 0; e < 4; ++e) if (n + e < g.N) atomicAdd(dst + e, xs[e] * sc);
+                continue;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float y = xs[e] * sc;
+                if (g.bias && n + e < g.N) y += g.bias[n + e];
+                if (g.act) y = y > 0.f ? y : y * g.slope;
+                xs[e] = y;
+            }
+            if (vec_ok && n + 3 < g.N) *(float4*)dst = make_float4(xs[0], xs[1], xs[2], xs[3]);
+            else for (int e = 0; e < 4; ++e) if (n + e < g.N) dst[e] = xs[e];
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
