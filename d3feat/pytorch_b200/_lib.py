@@ -36,6 +36,7 @@ SIGNATURES = {
     "d3f_kpconv_backward": (c_i, [c_p, c_p, c_p, c_i, c_i64, c_p, c_p, c_p, c_i, c_p,
                                   c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_i,
                                   c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "d3f_colsum": (c_i, [c_p, c_i, c_i, c_p, c_p]),
     "d3f_max_pool_forward": (c_i, [c_p, c_p, c_i, c_i64, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
     "d3f_max_pool_backward": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
     "d3f_gather_rows_forward": (c_i, [c_p, c_p, c_i, c_i64, c_i, c_i, c_i, c_p, c_p]),

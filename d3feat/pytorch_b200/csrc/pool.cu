@@ -217,7 +217,38 @@ __global__ void ds_gmax_backward_kernel(const unsigned long long* __restrict__ p
     if (garg >= 0) gF[garg] += *gacc;
 }
 
+// out[n] = sum_m x[m, n]   (bias gradients of the fused UnaryBlock; blocks.py:473 / nn.Linear bias)
+__global__ void colsum_kernel(const float* __restrict__ x, int M, int N, int rows_per_cta, float* __restrict__ out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int m0 = blockIdx.y * rows_per_cta, m1 = min(M, m0 + rows_per_cta);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int m = m0;
+    for (; m + 3 < m1; m += 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] += x[(size_t)(m + j) * N + n];
+    }
+    for (; m < m1; ++m) acc[0] += x[(size_t)m * N + n];
+    atomicAdd(&out[n], (acc[0] + acc[1]) + (acc[2] + acc[3]));
+}
+
 }  // namespace
+
+extern "C" int d3f_colsum(const float* x, int n_rows, int n_cols, float* out, d3f_stream stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    D3F_REQUIRE(n_rows >= 0 && n_cols >= 1 && out, D3F_ERR_INVALID, "bad arguments");
+    D3F_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * n_cols, stream));
+    if (n_rows == 0) return D3F_OK;
+    D3F_REQUIRE(x, D3F_ERR_INVALID, "null pointer");
+    const int col_ctas = d3f_ceil_div(n_cols, 128);
+    int row_ctas = d3f_ceil_div(592, col_ctas);                  // ~4 CTAs per SM
+    int rpc = d3f_ceil_div(n_rows, row_ctas);
+    if (rpc < 32) rpc = 32;
+    row_ctas = d3f_ceil_div(n_rows, rpc);
+    colsum_kernel<<<dim3(col_ctas, row_ctas), 128, 0, stream>>>(x, n_rows, n_cols, rpc, out);
+    D3F_CHECK_LAUNCH();
+    return D3F_OK;
+}
 
 extern "C" int d3f_max_pool_forward(const float* x, const void* inds, int idx_is_64, int64_t ld_inds, int n_queries,
                                     int n_supports, int n_neighbors, int channels, float* out, int32_t* argmax,

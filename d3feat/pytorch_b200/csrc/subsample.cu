@@ -28,6 +28,11 @@ constexpr int SM_SORT_CAP = 16384;   // entries of the shared-memory sort buffer
 constexpr int SM_FT_CAP = 20753;     // bucket counts up to this prime fit the shared first-touch array
 constexpr uint32_t R20 = (1u << 20) - 1u;
 
+// bucket of a voxel key (identity hash, key % bucket_count); 32-bit fast path (64-bit '%' is a long software loop)
+__device__ __forceinline__ uint32_t bucket_of(unsigned long long key, uint32_t nbkt) {
+    return key <= 0xFFFFFFFFull ? (uint32_t)key % nbkt : (uint32_t)(key % nbkt);
+}
+
 __constant__ unsigned int c_primes[24] = {13, 29, 59, 127, 257, 541, 1109, 2357, 5087, 10273, 20753,
                                           42043, 85229, 172933, 351061, 712697, 1447153, 2938679,
                                           5967347, 12117689, 24607243, 0, 0, 0};
@@ -232,7 +237,7 @@ sub_order_kernel(const int32_t* __restrict__ len, int nb, const unsigned long lo
         for (uint32_t q = tid; q < nbkt; q += ORDER_THREADS) ft[q] = 0xFFFFFFFFu;
         __syncthreads();
         for (uint32_t p = tid; p < L; p += ORDER_THREADS)
-            atomicMin(&ft[(uint32_t)(ck[seq[p]] % nbkt)], p);
+            atomicMin(&ft[bucket_of(ck[seq[p]], nbkt)], p);
         __syncthreads();
         uint32_t n2 = 1;
         while (n2 < L) n2 <<= 1;
@@ -240,7 +245,7 @@ sub_order_kernel(const int32_t* __restrict__ len, int nb, const unsigned long lo
             unsigned long long k = ~0ULL;
             if (p < L) {
                 const uint32_t e = seq[p];
-                const uint32_t f = ft[(uint32_t)(ck[e] % nbkt)];
+                const uint32_t f = ft[bucket_of(ck[e], nbkt)];
                 k = ((unsigned long long)(R20 - f) << 40) | ((unsigned long long)(R20 - p) << 20) | e;
             }
             buf[p] = k;

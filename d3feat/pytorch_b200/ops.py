@@ -414,6 +414,15 @@ def gemm(a, b, trans_a=False, trans_b=False, row_scale=None, k_scale=None, bias=
     return c
 
 
+def colsum(x):
+    """x.sum(dim=0) for a 2-D fp32 CUDA tensor (d3f_colsum)."""
+    lib = _lib.load()
+    x = _cuda_f32(x, "x")
+    out = torch.empty(x.shape[1], dtype=torch.float32, device=x.device)
+    _lib.check(lib.d3f_colsum(_p(x), x.shape[0], x.shape[1], _p(out), _stream()))
+    return out
+
+
 class _FusedLinear(torch.autograd.Function):
     """y = LeakyReLU_slope(x @ W^T + b)  (slope None: no activation) -- the UnaryBlock body
     (models/blocks.py:505-510 with use_bn=False) as one GEMM with a fused epilogue."""
@@ -432,7 +441,7 @@ class _FusedLinear(torch.autograd.Function):
         dz = dz.contiguous()
         dx = gemm(dz, weight) if ctx.needs_input_grad[0] else None                 # [M,out] @ [out,in]
         dw = gemm(dz, x, trans_a=True) if ctx.needs_input_grad[1] else None         # dz^T [out,M] @ x [M,in]
-        db = dz.sum(dim=0) if ctx.needs_input_grad[2] else None
+        db = colsum(dz) if ctx.needs_input_grad[2] else None
         return dx, dw, db, None
 
 

@@ -179,6 +179,8 @@ int d3f_pair_loss_backward(const float* anchor, const float* positive, int P, in
  *                 gmax_state: 16-byte device scratch written by forward and read by backward.
  * Backward entry points fully overwrite their grad_* output.
  */
+/* out[n] = sum over rows of x[n_rows, n_cols] (bias gradients of the fused UnaryBlock) */
+int d3f_colsum(const float* x, int n_rows, int n_cols, float* out, d3f_stream stream);
 int d3f_max_pool_forward(const float* x, const void* inds, int idx_is_64, int64_t ld_inds, int n_queries,
                          int n_supports, int n_neighbors, int channels, float* out, int32_t* argmax,
                          d3f_stream stream);
