@@ -18,9 +18,13 @@ __device__ __forceinline__ long long load_idx(const void* p, size_t off) {
 // ------------------------------------------------------------------------------------------- max pool
 template <bool IDX64>
 __global__ void mp_forward_kernel(const float* __restrict__ x, const void* __restrict__ inds, long long ld, int nq,
-                                  int ns, int H, int C, float* __restrict__ out, int* __restrict__ arg) {
+                                  int ns, int H, int C, float* __restrict__ out, int* __restrict__ arg,
+                                  const int* __restrict__ valid_width) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= nq) return;
+    // columns >= *valid_width do not exist in the reference's matrix (its width is min(max_count, limit)): they
+    // must not contribute the zero shadow row to the max
+    if (valid_width) H = min(H, max(*valid_width, 0));
     for (int c0 = 0; c0 < C; c0 += 128) {
         const int c = c0 + lane * 4;
         float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -116,9 +120,11 @@ __device__ __forceinline__ float ds_sigmoid(float v) { return v > 20.0f ? 1.0f :
 template <bool IDX64, bool BACKWARD>
 __global__ void ds_kernel(const float* __restrict__ F, const void* __restrict__ nb, long long ld, int n, int H, int C,
                           const unsigned long long* __restrict__ packed, int eval_mode, float* __restrict__ score,
-                          const float* __restrict__ gscore, float* __restrict__ gF, float* __restrict__ gacc) {
+                          const float* __restrict__ gscore, float* __restrict__ gF, float* __restrict__ gacc,
+                          const int* __restrict__ valid_width) {
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= n) return;
+    if (valid_width) H = min(H, max(*valid_width, 0));
     long long garg;
     const float inv = 1.0f / (ds_unpack_max(*packed, &garg) + 1e-6f);
     float gs = 0.f;
@@ -251,15 +257,15 @@ extern "C" int d3f_colsum(const float* x, int n_rows, int n_cols, float* out, d3
 }
 
 extern "C" int d3f_max_pool_forward(const float* x, const void* inds, int idx_is_64, int64_t ld_inds, int n_queries,
-                                    int n_supports, int n_neighbors, int channels, float* out, int32_t* argmax,
-                                    d3f_stream stream_) {
+                                    int n_supports, int n_neighbors, int channels, const int32_t* valid_width,
+                                    float* out, int32_t* argmax, d3f_stream stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     D3F_REQUIRE(n_queries >= 0 && n_supports >= 0 && n_neighbors >= 0 && channels >= 1, D3F_ERR_INVALID, "bad sizes");
     if (n_queries == 0) return D3F_OK;
     D3F_REQUIRE(x && (inds || n_neighbors == 0) && out && argmax, D3F_ERR_INVALID, "null pointer");
     auto kern = idx_is_64 ? mp_forward_kernel<true> : mp_forward_kernel<false>;
     kern<<<d3f_ceil_div(n_queries, 8), 256, 0, stream>>>(x, inds, (long long)ld_inds, n_queries, n_supports, n_neighbors,
-                                                        channels, out, argmax);
+                                                        channels, out, argmax, valid_width);
     D3F_CHECK_LAUNCH();
     return D3F_OK;
 }
@@ -308,7 +314,8 @@ extern "C" int d3f_gather_rows_backward(const float* grad_out, const void* idx, 
 
 extern "C" int d3f_detection_scores_forward(const float* features, const void* neighbors, int idx_is_64,
                                             int64_t ld_inds, int n_points, int n_neighbors, int channels,
-                                            int eval_mode, float* scores, void* gmax_state, d3f_stream stream_) {
+                                            int eval_mode, const int32_t* valid_width, float* scores,
+                                            void* gmax_state, d3f_stream stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     D3F_REQUIRE(n_points >= 0 && n_neighbors >= 0, D3F_ERR_INVALID, "bad sizes");
     D3F_REQUIRE(channels >= 1 && channels <= 32, D3F_ERR_UNSUPPORTED, "detection scores support up to 32 channels");
@@ -322,15 +329,15 @@ extern "C" int d3f_detection_scores_forward(const float* features, const void* n
     auto kern = idx_is_64 ? ds_kernel<true, false> : ds_kernel<false, false>;
     kern<<<d3f_ceil_div(n_points, 8), 256, 0, stream>>>(features, neighbors, (long long)ld_inds, n_points, n_neighbors,
                                                        channels, (const unsigned long long*)gmax_state, eval_mode,
-                                                       scores, nullptr, nullptr, nullptr);
+                                                       scores, nullptr, nullptr, nullptr, valid_width);
     D3F_CHECK_LAUNCH();
     return D3F_OK;
 }
 
 extern "C" int d3f_detection_scores_backward(const float* features, const void* neighbors, int idx_is_64,
                                              int64_t ld_inds, int n_points, int n_neighbors, int channels,
-                                             int eval_mode, const void* gmax_state, const float* grad_scores,
-                                             float* grad_features, d3f_stream stream_) {
+                                             int eval_mode, const int32_t* valid_width, const void* gmax_state,
+                                             const float* grad_scores, float* grad_features, d3f_stream stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     D3F_REQUIRE(n_points >= 0 && n_neighbors >= 0, D3F_ERR_INVALID, "bad sizes");
     D3F_REQUIRE(channels >= 1 && channels <= 32, D3F_ERR_UNSUPPORTED, "detection scores support up to 32 channels");
@@ -343,7 +350,7 @@ extern "C" int d3f_detection_scores_backward(const float* features, const void* 
     auto kern = idx_is_64 ? ds_kernel<true, true> : ds_kernel<false, true>;
     kern<<<d3f_ceil_div(n_points, 8), 256, 0, stream>>>(features, neighbors, (long long)ld_inds, n_points, n_neighbors,
                                                        channels, (const unsigned long long*)gmax_state, eval_mode,
-                                                       nullptr, grad_scores, grad_features, gacc);
+                                                       nullptr, grad_scores, grad_features, gacc, valid_width);
     D3F_CHECK_LAUNCH();
     ds_gmax_backward_kernel<<<1, 1, 0, stream>>>((const unsigned long long*)gmax_state, gacc, grad_features);
     D3F_CHECK_LAUNCH();

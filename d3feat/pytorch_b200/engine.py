@@ -54,6 +54,9 @@ def collate_static(pts0, pts1, feat0, feat1, corr, dist_keypts, config, limits, 
     def search(q, s, ql, sl, r, limit, pad):
         idx, info = ops.radius_neighbors_raw(q, s, ql, sl, r, int(limit), torch.int32, None, False, pad_index=pad)
         flags.append(info[1:2])           # 1 = a row overflowed the candidate buffer
+        # the reference's matrix has min(max_count, limit) columns (dataloader.py:64-65): a row that fills it holds
+        # no shadow index, which max_pool / the eval-mode detection gate can see -> keep that width on the device
+        idx._d3f_width = torch.clamp(info[0:1], max=int(limit))
         return idx
 
     for bi, block in enumerate(arch):

@@ -279,9 +279,15 @@ def _idx(t, name):
     return t
 
 
+def _valid_width(inds):
+    """Device int32 tensor holding the reference's matrix width for a capacity-padded neighbour matrix
+    (set by engine.collate_static), or None for exact-shape matrices."""
+    return getattr(inds, "_d3f_width", None)
+
+
 class _MaxPool(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, inds):
+    def forward(ctx, x, inds, width):
         lib = _lib.load()
         x, inds = _cuda_f32(x, "x"), _idx(inds, "inds")
         if inds.stride(-1) != 1:
@@ -294,7 +300,8 @@ class _MaxPool(torch.autograd.Function):
         launch_count += 1
         with _Timed(("max_pool", nq, ns, H, C)):
             _lib.check(lib.d3f_max_pool_forward(_p(x), _p(inds), 1 if inds.dtype == torch.int64 else 0,
-                                                inds.stride(0) if H > 0 else 0, nq, ns, H, C, _p(out), _p(arg), _stream()))
+                                                inds.stride(0) if H > 0 else 0, nq, ns, H, C, _p(width), _p(out), _p(arg),
+                                                _stream()))
         ctx.save_for_backward(arg)
         ctx.shape = (nq, ns, C)
         return out
@@ -308,7 +315,7 @@ class _MaxPool(torch.autograd.Function):
         gx = torch.empty((ns, C), dtype=torch.float32, device=g.device)
         with _Timed(("max_pool_bwd", nq, ns, C)):
             _lib.check(lib.d3f_max_pool_backward(_p(g), _p(arg), nq, ns, C, _p(gx), _stream()))
-        return gx, None
+        return gx, None, None
 
 
 class _GatherRows(torch.autograd.Function):
@@ -345,7 +352,7 @@ class _GatherRows(torch.autograd.Function):
 
 class _DetectionScores(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, feats, neighbors, eval_mode):
+    def forward(ctx, feats, neighbors, eval_mode, width):
         lib = _lib.load()
         feats, neighbors = _cuda_f32(feats, "features"), _idx(neighbors, "neighbors")
         if neighbors.stride(-1) != 1:
@@ -359,15 +366,15 @@ class _DetectionScores(torch.autograd.Function):
         with _Timed(("det_scores", n, H, C)):
             _lib.check(lib.d3f_detection_scores_forward(_p(feats), _p(neighbors), 1 if neighbors.dtype == torch.int64 else 0,
                                                         neighbors.stride(0) if H > 0 else 0, n, H, C, int(eval_mode),
-                                                        _p(scores), _p(state), _stream()))
-        ctx.save_for_backward(feats, neighbors, state)
+                                                        _p(width), _p(scores), _p(state), _stream()))
+        ctx.save_for_backward(feats, neighbors, state, width)
         ctx.eval_mode = int(eval_mode)
         return scores
 
     @staticmethod
     def backward(ctx, g):
         lib = _lib.load()
-        feats, neighbors, state = ctx.saved_tensors
+        feats, neighbors, state, width = ctx.saved_tensors
         n, C = feats.shape
         H = neighbors.shape[1]
         g = _cuda_f32(g.reshape(-1), "grad")
@@ -375,12 +382,12 @@ class _DetectionScores(torch.autograd.Function):
         with _Timed(("det_scores_bwd", n, H, C)):
             _lib.check(lib.d3f_detection_scores_backward(_p(feats), _p(neighbors), 1 if neighbors.dtype == torch.int64 else 0,
                                                          neighbors.stride(0) if H > 0 else 0, n, H, C, ctx.eval_mode,
-                                                         _p(state), _p(g), _p(gf), _stream()))
-        return gf, None, None
+                                                         _p(width), _p(state), _p(g), _p(gf), _stream()))
+        return gf, None, None, None
 
 
 def max_pool(x, inds):
-    return _MaxPool.apply(x, inds)
+    return _MaxPool.apply(x, inds, _valid_width(inds))
 
 
 def gather_rows(x, idx):
@@ -388,7 +395,7 @@ def gather_rows(x, idx):
 
 
 def detection_scores(feats, neighbors, eval_mode):
-    return _DetectionScores.apply(feats, neighbors, eval_mode)
+    return _DetectionScores.apply(feats, neighbors, eval_mode, _valid_width(neighbors))
 
 
 # --------------------------------------------------------------------------- tensor-core GEMM (3xTF32) + fused linear

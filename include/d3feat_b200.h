@@ -177,13 +177,16 @@ int d3f_pair_loss_backward(const float* anchor, const float* positive, int P, in
  * detection     : KPFCNN.detection_scores (models/architectures.py:322-368), train (eval_mode=0) or test
  *                 (eval_mode=1: exact-equality local-max gate); features [N,C<=32], neighbors [N,H];
  *                 gmax_state: 16-byte device scratch written by forward and read by backward.
+ * valid_width (device int32, may be NULL): the neighbour matrix may be allocated wider than the reference's
+ *                 matrix (static capacities); columns >= *valid_width are treated as absent, not as shadow
+ *                 neighbours (a row that fills the reference's matrix has no zero shadow row in its max).
  * Backward entry points fully overwrite their grad_* output.
  */
 /* out[n] = sum over rows of x[n_rows, n_cols] (bias gradients of the fused UnaryBlock) */
 int d3f_colsum(const float* x, int n_rows, int n_cols, float* out, d3f_stream stream);
 int d3f_max_pool_forward(const float* x, const void* inds, int idx_is_64, int64_t ld_inds, int n_queries,
-                         int n_supports, int n_neighbors, int channels, float* out, int32_t* argmax,
-                         d3f_stream stream);
+                         int n_supports, int n_neighbors, int channels, const int32_t* valid_width, float* out,
+                         int32_t* argmax, d3f_stream stream);
 int d3f_max_pool_backward(const float* grad_out, const int32_t* argmax, int n_queries, int n_supports,
                           int channels, float* grad_x, d3f_stream stream);
 int d3f_gather_rows_forward(const float* x, const void* idx, int idx_is_64, int64_t idx_stride, int n_rows,
@@ -191,12 +194,12 @@ int d3f_gather_rows_forward(const float* x, const void* idx, int idx_is_64, int6
 int d3f_gather_rows_backward(const float* grad_out, const void* idx, int idx_is_64, int64_t idx_stride,
                              int n_rows, int n_supports, int channels, float* grad_x, d3f_stream stream);
 int d3f_detection_scores_forward(const float* features, const void* neighbors, int idx_is_64, int64_t ld_inds,
-                                 int n_points, int n_neighbors, int channels, int eval_mode, float* scores,
-                                 void* gmax_state, d3f_stream stream);
+                                 int n_points, int n_neighbors, int channels, int eval_mode,
+                                 const int32_t* valid_width, float* scores, void* gmax_state, d3f_stream stream);
 int d3f_detection_scores_backward(const float* features, const void* neighbors, int idx_is_64, int64_t ld_inds,
                                   int n_points, int n_neighbors, int channels, int eval_mode,
-                                  const void* gmax_state, const float* grad_scores, float* grad_features,
-                                  d3f_stream stream);
+                                  const int32_t* valid_width, const void* gmax_state, const float* grad_scores,
+                                  float* grad_features, d3f_stream stream);
 
 /* ------------------------------------------------------------------------------------------
  * fp32-accurate tensor-core GEMM (3xTF32) with fused epilogue -- the dense contraction behind KPConv

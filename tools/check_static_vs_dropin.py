@@ -21,7 +21,7 @@ def hook(name):
     def f(mod, inp, out):
         if isinstance(out, torch.Tensor): acts.setdefault(name, []).append(out.detach().clone())
     return f
-hs = [m.register_forward_hook(hook(n)) for n, m in model.named_modules() if n and n.count(".") <= 1]
+hs = [m.register_forward_hook(hook(n)) for n, m in model.named_modules() if n and n.count(".") <= 3]
 def run(batch):
     feats, scores = model(batch)
     c = batch["corr"].long(); ia, ip = c[:, 0], c[:, 1] + 1500
@@ -45,8 +45,18 @@ for name, lst in acts.items():
     # real rows of a static tensor = first `size` rows at that level
     real = next((s for s, c in zip(sizes, caps) if c == b.shape[0]), n)
     d = (a[:real] - b[:real]).abs().max().item() if a.shape[0] >= real else float("nan")
-    if d != 0: bad += 1; print("FWD DIFF %-32s rows %d max abs %.2e" % (name, real, d))
+    if d != 0:
+        bad += 1
+        if bad <= 12: print("FWD DIFF %-40s rows %d max abs %.2e  (first bad row %s)" % (name, real, d, int(((a[:real]-b[:real]).abs().amax(dim=tuple(range(1,a.dim()))) > 0).nonzero()[0])))
 print("modules with forward differences:", bad, "of", len(acts))
+# direct op probes at the deepest strided block
+from d3feat.pytorch_b200 import ops
+xe = acts["encoder_blocks.10"][0]; xs_ = acts["encoder_blocks.10"][2]
+print("block10 out equal on real rows:", bool(torch.equal(xe[:sizes[3]], xs_[:sizes[3]])))
+mp_e = ops.max_pool(xe, exact["pools"][3]); mp_s = ops.max_pool(xs_, static["pools"][3])
+print("max_pool L3->4 equal:", bool(torch.equal(mp_e[:sizes[4]], mp_s[:sizes[4]])), "max abs", float((mp_e[:sizes[4]]-mp_s[:sizes[4]]).abs().max()))
+pe, ps = exact["pools"][3], static["pools"][3]
+print("pools[3] exact shape", tuple(pe.shape), "static", tuple(ps.shape), "exact max", int(pe.max()), "static real-row max", int(ps[:sizes[4]].max()))
 def cmp(x, y, name):
     w = sorted(((float((x[k]-y[k]).abs().max()/max(float(y[k].abs().max()),1e-30)), k) for k in x), reverse=True)[:3]
     print(name, ["%.1e %s" % t for t in w])
