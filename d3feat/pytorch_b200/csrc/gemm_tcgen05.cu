@@ -19,15 +19,19 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 64, BK = 32, NT = 256;
+constexpr int BM = 128, BK = 32, NT = 256;
 constexpr int SBO = 144;                              // stride between 8-row groups (128 + 16 pad)
 constexpr int A_LBO = (BM / 8) * SBO + 16;            // stride between 16-byte k units: 2320
-constexpr int B_LBO = (BN / 8) * SBO + 16;            // 1168
 constexpr int A_TILE = (BK / 4) * A_LBO;              // 18560
-constexpr int B_TILE = (BK / 4) * B_LBO;              // 9344
-constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;  // hi + lo for A and B = 55808
-constexpr int SMEM_BYTES = 2 * STAGE_BYTES + 64;      // two stages + barriers / tmem pointer
-constexpr uint32_t TMEM_COLS = 64;
+// the N tile is a template parameter (32 / 64 / 128): skinny outputs do not pay for a half-empty MMA and wide ones
+// re-read A half as often
+template <int BN> struct Cfg {
+    static constexpr int B_LBO = (BN / 8) * SBO + 16;
+    static constexpr int B_TILE = (BK / 4) * B_LBO;
+    static constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;   // hi + lo for A and B
+    static constexpr int SMEM_BYTES = 2 * STAGE_BYTES + 64;       // two stages + barriers / tmem pointer
+    static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -78,9 +82,11 @@ __device__ __forceinline__ void st_split(char* hi, char* lo, uint32_t off, float
 
 __device__ int g_tc5_fail = 0;
 
-template <bool TA, bool TB>
+template <bool TA, bool TB, int BN>
 __global__ void __launch_bounds__(NT)
 tc5_gemm_kernel(D3fGemm g) {
+    constexpr int B_LBO = Cfg<BN>::B_LBO, B_TILE = Cfg<BN>::B_TILE, STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
+    constexpr uint32_t TMEM_COLS = Cfg<BN>::TMEM_COLS;
     extern __shared__ __align__(128) char smem[];
     uint64_t* bars = (uint64_t*)(smem + 2 * STAGE_BYTES);      // [0],[1]: stage free (MMA done);  [2]: all MMAs done
     uint32_t* tmem_ptr = (uint32_t*)(smem + 2 * STAGE_BYTES + 32);
@@ -110,7 +116,7 @@ tc5_gemm_kernel(D3fGemm g) {
     // (both operands are fed K-major: a_major = b_major = 0)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-    float4 ra[4], rb[4];
+    float4 ra[4], rb[BN >= 128 ? BN / 32 : 4];
     auto load_tile = [&](int k0) {
         if (!TA) {      // A[m][k]: thread = (row, 16-byte k unit)
 #pragma unroll
@@ -127,14 +133,14 @@ tc5_gemm_kernel(D3fGemm g) {
         }
         if (TB) {       // B[n][k]
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
+            for (int r = 0; r < BN / 32; ++r) {
                 const int n = n0 + (tid >> 3) + 32 * r, k = k0 + (tid & 7) * 4;
                 rb[r] = (n < g.N) ? ld4g(g.B + (size_t)n * g.ldb + k, kend - k, b_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-        } else if (tid < 128) {   // B[k][n]: thread = (4 k rows, 4 consecutive n)
+        } else if (tid < 2 * BN) {   // B[k][n]: thread = (4 k rows, 4 consecutive n)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int k = k0 + (tid >> 4) * 4 + j, n = n0 + (tid & 15) * 4;
+                const int k = k0 + (tid / (BN / 4)) * 4 + j, n = n0 + (tid % (BN / 4)) * 4;
                 float4 v = (k < kend) ? ld4g(g.B + (size_t)k * g.ldb + n, g.N - n, b_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
                 if (g.ks && k < kend) { const float sc = g.ks[k]; v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc; }
                 rb[j] = v;
@@ -164,12 +170,12 @@ tc5_gemm_kernel(D3fGemm g) {
         }
         if (TB) {
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
+            for (int r = 0; r < BN / 32; ++r) {
                 const int n = (tid >> 3) + 32 * r, k4 = tid & 7;
                 st_split(b_hi, b_lo, k4 * B_LBO + (n >> 3) * SBO + (n & 7) * 16, rb[r]);
             }
-        } else if (tid < 128) {
-            const int k4 = tid >> 4, nb = (tid & 15) * 4;
+        } else if (tid < 2 * BN) {
+            const int k4 = tid / (BN / 4), nb = (tid % (BN / 4)) * 4;
             const float t[4][4] = {{rb[0].x, rb[1].x, rb[2].x, rb[3].x}, {rb[0].y, rb[1].y, rb[2].y, rb[3].y},
                                    {rb[0].z, rb[1].z, rb[2].z, rb[3].z}, {rb[0].w, rb[1].w, rb[2].w, rb[3].w}};
 #pragma unroll
@@ -220,11 +226,11 @@ tc5_gemm_kernel(D3fGemm g) {
     constexpr int LDC_S = BN + 4;
     float* cs = (float*)smem;                       // the operand stages are free once bars[2] has completed
     {
-        const int r_loc = (warp & 3) * 32 + lane, col0 = (warp >> 2) * 32;
+        const int r_loc = (warp & 3) * 32 + lane, col0 = (warp >> 2) * (BN / 2);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        for (int part = 0; part < BN / 32; ++part) {
             uint32_t v[16];
-            const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(col0 + half * 16);
+            const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(col0 + part * 16);
             if (nk > 0) {
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
                              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
@@ -237,17 +243,18 @@ tc5_gemm_kernel(D3fGemm g) {
             }
 #pragma unroll
             for (int e = 0; e < 16; e += 4)
-                *(uint4*)&cs[r_loc * LDC_S + col0 + half * 16 + e] = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                *(uint4*)&cs[r_loc * LDC_S + col0 + part * 16 + e] = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
         }
     }
     __syncthreads();
     {
         const bool atomic = gridDim.z > 1 && !g.partial;
-        const int c4 = (tid & 15) * 4, n = n0 + c4;
+        constexpr int TPR = BN / 4, RPP = NT / TPR;      // threads per row, rows per pass
+        const int c4 = (tid % TPR) * 4, n = n0 + c4;
         const bool vec_ok = g.partial ? ((g.N & 3) == 0) : ((g.ldc & 3) == 0 && (((size_t)g.C) & 15) == 0);
 #pragma unroll
-        for (int it = 0; it < BM / 16; ++it) {
-            const int r_loc = (tid >> 4) + 16 * it, row = m0 + r_loc;
+        for (int it = 0; it < BM / RPP; ++it) {
+            const int r_loc = tid / TPR + RPP * it, row = m0 + r_loc;
             if (row >= g.M || n >= g.N) continue;
             float4 x = *(const float4*)&cs[r_loc * LDC_S + c4];
             float xs[4] = {x.x, x.y, x.z, x.w};
@@ -283,24 +290,34 @@ tc5_gemm_kernel(D3fGemm g) {
 }  // namespace
 
 // launched by d3f_gemm_launch (gemm.cu) with the split decision already made
-int d3f_gemm_tcgen05_launch(const D3fGemm& g, bool ta, bool tb, int splits, cudaStream_t stream) {
+template <bool TA, bool TB, int BN>
+static int launch_bn(const D3fGemm& g, int splits, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        D3F_CHECK_CUDA(cudaFuncSetAttribute(tc5_gemm_kernel<TA, TB, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            Cfg<BN>::SMEM_BYTES));
+        attr_set = true;
+    }
     dim3 grid(d3f_ceil_div(g.N, BN), d3f_ceil_div(g.M, BM), splits);
-#define LAUNCH5(TA_, TB_)                                                                                  \
-    do {                                                                                                   \
-        static bool attr_set = false;                                                                      \
-        if (!attr_set) {                                                                                   \
-            D3F_CHECK_CUDA(cudaFuncSetAttribute(tc5_gemm_kernel<TA_, TB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)); \
-            attr_set = true;                                                                               \
-        }                                                                                                  \
-        tc5_gemm_kernel<TA_, TB_><<<grid, NT, SMEM_BYTES, stream>>>(g);                                    \
-    } while (0)
-    if (ta && !tb) LAUNCH5(true, false);
-    else if (!ta && tb) LAUNCH5(false, true);
-    else if (!ta && !tb) LAUNCH5(false, false);
-    else { d3f_set_error("gemm: TT mode is not used on the hot path"); return D3F_ERR_UNSUPPORTED; }
-#undef LAUNCH5
+    tc5_gemm_kernel<TA, TB, BN><<<grid, NT, Cfg<BN>::SMEM_BYTES, stream>>>(g);
     D3F_CHECK_LAUNCH();
     return D3F_OK;
+}
+
+template <bool TA, bool TB>
+static int launch_mode(const D3fGemm& g, int splits, cudaStream_t stream) {
+    if (g.N <= 32) return launch_bn<TA, TB, 32>(g, splits, stream);
+    // wide outputs with enough row tiles to fill the chip: 128-wide tiles halve the A re-reads
+    if (g.N >= 256 && d3f_ceil_div(g.M, BM) * d3f_ceil_div(g.N, 128) * splits >= 148) return launch_bn<TA, TB, 128>(g, splits, stream);
+    return launch_bn<TA, TB, 64>(g, splits, stream);
+}
+
+int d3f_gemm_tcgen05_launch(const D3fGemm& g, bool ta, bool tb, int splits, cudaStream_t stream) {
+    if (ta && !tb) return launch_mode<true, false>(g, splits, stream);
+    if (!ta && tb) return launch_mode<false, true>(g, splits, stream);
+    if (!ta && !tb) return launch_mode<false, false>(g, splits, stream);
+    d3f_set_error("gemm: TT mode is not used on the hot path");
+    return D3F_ERR_UNSUPPORTED;
 }
 
 // 1 if any tcgen05 GEMM gave up waiting on an mbarrier (diagnostic; reads a device symbol -> synchronises)
