@@ -29,7 +29,10 @@ template <int BN> struct Cfg {
     static constexpr int B_LBO = (BN / 8) * SBO + 16;
     static constexpr int B_TILE = (BK / 4) * B_LBO;
     static constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;   // hi + lo for A and B
-    static constexpr int SMEM_BYTES = 2 * STAGE_BYTES + 64;       // two stages + barriers / tmem pointer
+    // ONE shared-memory stage: these GEMMs are short (K = 32..960 for most of them) and latency-bound, so the
+    // latency is hidden by co-resident CTAs (4 per SM at 46-56 KB) rather than by a deep pipeline inside one CTA
+    // (ncu, round 1: 2 stages -> 1-2 CTAs/SM, 12-22 % warps active, every pipe under 27 %).
+    static constexpr int SMEM_BYTES = STAGE_BYTES + 64;           // one stage + barrier / tmem pointer
     static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
 };
 
@@ -83,13 +86,13 @@ __device__ __forceinline__ void st_split(char* hi, char* lo, uint32_t off, float
 __device__ int g_tc5_fail = 0;
 
 template <bool TA, bool TB, int BN>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, BN >= 128 ? 3 : 4)
 tc5_gemm_kernel(D3fGemm g) {
     constexpr int B_LBO = Cfg<BN>::B_LBO, B_TILE = Cfg<BN>::B_TILE, STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
     constexpr uint32_t TMEM_COLS = Cfg<BN>::TMEM_COLS;
     extern __shared__ __align__(128) char smem[];
-    uint64_t* bars = (uint64_t*)(smem + 2 * STAGE_BYTES);      // [0],[1]: stage free (MMA done);  [2]: all MMAs done
-    uint32_t* tmem_ptr = (uint32_t*)(smem + 2 * STAGE_BYTES + 32);
+    uint64_t* bars = (uint64_t*)(smem + STAGE_BYTES);          // [0]: the MMAs of the current K tile are done
+    uint32_t* tmem_ptr = (uint32_t*)(smem + STAGE_BYTES + 32);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int kbeg = blockIdx.z * g.k_per_split, kend = min(g.K, kbeg + g.k_per_split);
@@ -102,8 +105,7 @@ tc5_gemm_kernel(D3fGemm g) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
     if (tid == 32) {
-        for (int i = 0; i < 3; ++i)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(&bars[i])), "r"(1) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(&bars[0])), "r"(1) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -147,8 +149,8 @@ tc5_gemm_kernel(D3fGemm g) {
             }
         }
     };
-    auto store_tile = [&](int stage) {
-        char* a_hi = smem + stage * STAGE_BYTES;
+    auto store_tile = [&]() {
+        char* a_hi = smem;
         char* a_lo = a_hi + A_TILE;
         char* b_hi = a_lo + A_TILE;
         char* b_lo = b_hi + B_TILE;
@@ -188,16 +190,15 @@ tc5_gemm_kernel(D3fGemm g) {
 
     if (nk > 0) load_tile(kbeg);
     for (int kt = 0; kt < nk; ++kt) {
-        const int stage = kt & 1;
-        if (kt >= 2) mbar_wait(smem_u32(&bars[stage]), ((kt >> 1) - 1) & 1, &g_tc5_fail);   // MMAs of tile kt-2 released this stage
-        store_tile(stage);
-        if (kt + 1 < nk) load_tile(kbeg + (kt + 1) * BK);                                     // global loads overlap the MMAs
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");                         // generic-proxy stores -> async proxy (UMMA)
+        if (kt >= 1) mbar_wait(smem_u32(&bars[0]), (kt - 1) & 1, &g_tc5_fail);   // MMAs of tile kt-1 have read the stage
+        store_tile();
+        if (kt + 1 < nk) load_tile(kbeg + (kt + 1) * BK);                          // global loads overlap the MMAs
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");              // generic-proxy stores -> async proxy (UMMA)
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
         __syncthreads();
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            const uint32_t a_hi = smem_u32(smem + stage * STAGE_BYTES), a_lo = a_hi + A_TILE;
+            const uint32_t a_hi = smem_u32(smem), a_lo = a_hi + A_TILE;
             const uint32_t b_hi = a_lo + A_TILE, b_lo = b_hi + B_TILE;
 #pragma unroll
             for (int ks = 0; ks < BK / 8; ++ks) {
@@ -211,15 +212,12 @@ tc5_gemm_kernel(D3fGemm g) {
             }
             // tcgen05.commit: arrive on the barrier when every MMA issued so far has completed
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
-                         :: "r"(smem_u32(&bars[stage])) : "memory");
-            if (kt == nk - 1)
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
-                             :: "r"(smem_u32(&bars[2])) : "memory");
+                         :: "r"(smem_u32(&bars[0])) : "memory");
         }
     }
 
-    // ---- epilogue: warp w reads TMEM lanes 32*(w%4) .. +31 (its row quarter), columns 32*(w/4) .. +31
-    if (nk > 0) mbar_wait(smem_u32(&bars[2]), 0, &g_tc5_fail);
+    // ---- epilogue
+    if (nk > 0) mbar_wait(smem_u32(&bars[0]), (nk - 1) & 1, &g_tc5_fail);
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     // TMEM -> registers (one row per thread) -> shared C tile [128][BN+4] (row stride = 4 banks mod 32: the
     // 128-bit stores of a quarter warp are conflict-free) -> 128-bit row-contiguous global stores.
