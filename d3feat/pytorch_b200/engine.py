@@ -180,6 +180,14 @@ class PairStep:
                 self._body()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        # deformable KPConv modules keep graph tensors of the last forward (deformed_KP, offset_features: the
+        # reference API for its regulariser); left alive they pin the warm-up iteration's autograd graph and
+        # its AccumulateGrad nodes, which belong to another stream and would invalidate the capture
+        for m in self.model.modules():
+            if hasattr(m, "deformed_KP"):
+                m.deformed_KP = m.offset_features = m.min_d2 = None
+        self.batch = None
+        gc.collect()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._body()
