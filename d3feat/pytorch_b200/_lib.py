@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_PKG, "libd3feat_b200.so")
 CSRC = os.path.join(_PKG, "csrc")
 HEADER = os.path.join(os.path.dirname(os.path.dirname(_PKG)), "include", "d3feat_b200.h")
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--threads", "0",
               "-Xcompiler", "-fPIC", "-shared"]
 
 c_p, c_i, c_f, c_d, c_sz, c_i64 = (ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_double,
@@ -36,6 +36,8 @@ SIGNATURES = {
     "d3f_kpconv_backward": (c_i, [c_p, c_p, c_p, c_i, c_i64, c_p, c_p, c_p, c_i, c_p,
                                   c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_i,
                                   c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "d3f_set_kpconv_impl": (None, [c_i]),
+    "d3f_get_kpconv_impl": (c_i, []),
     "d3f_colsum": (c_i, [c_p, c_i, c_i, c_p, c_p]),
     "d3f_max_pool_forward": (c_i, [c_p, c_p, c_i, c_i64, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "d3f_max_pool_backward": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p]),

@@ -16,6 +16,8 @@
 //   kp_scatter    : one warp per query: dx[idx] += sum_k w dwf  (+ kernel-point / modulation grads)
 #include "common.cuh"
 #include "gemm.cuh"
+#include "kpconv.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -503,6 +505,19 @@ int kp_set_smem(Kern kern, size_t smem) {
 
 }  // namespace
 
+// Gather-kernel generation: 0 = v1 (this file), 1 = v2 with FFMA accumulation, 2 = v2 with mma.sync 3xTF32
+// accumulation (kpconv2.cu).  Default from D3F_KPCONV_IMPL = v1 | ffma | mma, else v2/MMA.
+static int g_kp_impl = -1;
+extern "C" void d3f_set_kpconv_impl(int impl) { g_kp_impl = impl < 0 ? -1 : (impl > 2 ? 2 : impl); }
+static int kp_impl() {
+    if (g_kp_impl < 0) {
+        const char* e = getenv("D3F_KPCONV_IMPL");
+        g_kp_impl = !e ? 2 : (e[0] == 'v' ? 0 : (e[0] == 'f' ? 1 : 2));
+    }
+    return g_kp_impl;
+}
+extern "C" int d3f_get_kpconv_impl(void) { return kp_impl(); }
+
 extern "C" size_t d3f_kpconv_workspace_bytes(int n_queries, int n_supports, int n_neighbors, int K, int c_in,
                                              int c_out) {
     (void)n_neighbors;
@@ -533,11 +548,18 @@ extern "C" int d3f_kpconv_forward(const float* q_pts, const float* s_pts, const 
     }
     KpArgs a{q_pts, s_pts, inds, (long long)ld_inds, x, kernel_points, modulations, w.rowpos,
              nq, ns, H, K, cin, kp_extent, influence, aggregation};
-    size_t smem;
-    const int warps = kp_warps_per_cta(H, false, &smem);
-    const int grid = d3f_ceil_div(nq, warps);
-    KP_DISPATCH_ALL(kp_correlate_kernel, a, wf, wf_unmod, inv_n, deformed ? min_d2 : nullptr);
-    D3F_CHECK_LAUNCH();
+    if (kp_impl() >= 1 && kp2_supported(H, ns, cin)) {
+        Kp2Args a2{q_pts, s_pts, inds, (long long)ld_inds, x, kernel_points, modulations, w.rowpos,
+                   nq, ns, H, K, cin, kp_extent, influence, aggregation, idx_is_64 ? 1 : 0, deformed ? 1 : 0};
+        rc = kp2_correlate_launch(a2, wf, wf_unmod, inv_n, deformed ? min_d2 : nullptr, kp_impl() == 2 ? 1 : 0, stream);
+        if (rc) return rc;
+    } else {
+        size_t smem;
+        const int warps = kp_warps_per_cta(H, false, &smem);
+        const int grid = d3f_ceil_div(nq, warps);
+        KP_DISPATCH_ALL(kp_correlate_kernel, a, wf, wf_unmod, inv_n, deformed ? min_d2 : nullptr);
+        D3F_CHECK_LAUNCH();
+    }
     D3fGemm g{nq, cout, K * cin, wf, K * cin, weights, cout, out, cout, inv_n, nullptr, nullptr, 0, 0.f, 0, nullptr};
     // forward: deterministic, padding-independent split-K (a 1e-7 perturbation here can flip a LeakyReLU mask)
     float dummy;
@@ -587,6 +609,12 @@ extern "C" int d3f_kpconv_backward(const float* q_pts, const float* s_pts, const
     }
     KpArgs a{q_pts, s_pts, inds, (long long)ld_inds, x, kernel_points, modulations, w.rowpos,
              nq, ns, H, K, cin, kp_extent, influence, aggregation};
+    if (kp_impl() >= 1 && kp2_supported(H, ns, cin)) {
+        Kp2Args a2{q_pts, s_pts, inds, (long long)ld_inds, x, kernel_points, modulations, w.rowpos,
+                   nq, ns, H, K, cin, kp_extent, influence, aggregation, idx_is_64 ? 1 : 0, deformed ? 1 : 0};
+        return kp2_scatter_launch(a2, w.dwf, wf_unmod, grad_x, deformed ? grad_kernel_points : nullptr,
+                                  deformed ? grad_modulations : nullptr, stream);
+    }
     size_t smem;
     const int warps = kp_warps_per_cta(H, true, &smem);
     const int grid = d3f_ceil_div(nq, warps);

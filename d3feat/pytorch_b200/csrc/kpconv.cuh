@@ -1,0 +1,18 @@
+// Internal interface between kpconv.cu (C ABI, GEMM wiring, v1 kernels) and kpconv2.cu (v2 gather kernels).
+#pragma once
+#include <cuda_runtime.h>
+
+struct Kp2Args {
+    const float* q; const float* s; const void* inds; long long ld; const float* x;
+    const float* kp; const float* mod; const unsigned char* rowpos;
+    int nq, ns, H, K, cin; float extent; int influence, aggregation;
+    int idx64, deformed;
+};
+
+// mode: 0 = FFMA accumulation, 1 = mma.sync 3xTF32 accumulation (needs cin % 4 == 0 and 16-byte aligned x / wf)
+int kp2_correlate_launch(const Kp2Args& a, float* wf, float* wf_unmod, float* inv_n, float* min_d2, int mode,
+                         cudaStream_t stream);
+int kp2_scatter_launch(const Kp2Args& a, const float* dwf, const float* wf_unmod, float* grad_x, float* grad_kp,
+                       float* grad_mod, cudaStream_t stream);
+// the v2 kernels need one warp's shared-memory slab to fit and 32-bit row offsets (Ns * Cin < 2^31)
+bool kp2_supported(int H, int ns, int cin);

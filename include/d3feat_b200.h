@@ -119,6 +119,13 @@ int d3f_kpconv_forward(const float* q_pts, const float* s_pts, const void* inds,
                        float* out, float* wf, float* wf_unmod, float* inv_n, float* min_d2,
                        void* workspace, size_t workspace_bytes, d3f_stream stream);
 
+/* Gather-kernel generation used by d3f_kpconv_forward/_backward: 0 = v1 (warp per query, lanes over neighbours),
+ * 1 = v2 with FFMA accumulation, 2 = v2 with mma.sync 3xTF32 accumulation (csrc/kpconv2.cu); -1 restores the default
+ * (environment D3F_KPCONV_IMPL = v1 | ffma | mma, else 2).  All three compute the same function; the selector
+ * exists for A/B measurements and parity tests. */
+void d3f_set_kpconv_impl(int impl);
+int d3f_get_kpconv_impl(void);
+
 /* backward: grad_out [Nq,Cout] ->
  *   grad_x [Ns,Cin] or NULL (fully overwritten), grad_weights [K,Cin,Cout] or NULL (overwritten),
  *   grad_kernel_points [Nq,K,3] or NULL (deformed only), grad_modulations [Nq,K] or NULL. */

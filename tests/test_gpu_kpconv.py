@@ -10,6 +10,15 @@ from _util import rel_err
 pytestmark = pytest.mark.gpu
 TOL = 1e-4  # BASELINE.json north_star: descriptors and loss within 1e-4 relative, fp32
 
+
+@pytest.fixture(params=[0, 1, 2], ids=["v1", "v2-ffma", "v2-mma"])
+def kp_impl(request, built_lib):
+    """Every KPConv parity case runs on all three gather-kernel generations (d3f_set_kpconv_impl)."""
+    built_lib.d3f_set_kpconv_impl(request.param)
+    assert built_lib.d3f_get_kpconv_impl() == request.param
+    yield request.param
+    built_lib.d3f_set_kpconv_impl(-1)
+
 CASES = [
     ("kpconv_rigid_2k", 2000, 64, 64, False, False, "linear", "sum", 100),
     ("kpconv_rigid_c1", 1500, 1, 64, False, False, "linear", "sum", 101),
@@ -23,7 +32,7 @@ CASES = [
 
 @pytest.mark.parametrize("name,n,cin,cout,deform,mod,infl,agg,seed", CASES)
 @pytest.mark.parametrize("idx_dtype", [torch.int64, torch.int32])
-def test_kpconv_module_vs_reference_fixture(cuda, name, n, cin, cout, deform, mod, infl, agg, seed, idx_dtype):
+def test_kpconv_module_vs_reference_fixture(cuda, kp_impl, name, n, cin, cout, deform, mod, infl, agg, seed, idx_dtype):
     from d3feat.pytorch_b200.blocks import KPConv
     g = golden(name)
     case = _inputs.kpconv_case(n=n, cin=cin, cout=cout, seed=seed, deformable=deform, modulated=mod)
@@ -49,8 +58,10 @@ def test_kpconv_module_vs_reference_fixture(cuda, name, n, cin, cout, deform, mo
 
 
 @pytest.mark.parametrize("nq,ns,H,cin,cout", [(1, 1, 1, 1, 1), (37, 50, 7, 3, 45), (300, 200, 40, 33, 64),
-                                              (129, 257, 19, 130, 17), (64, 64, 48, 256, 128), (5, 9, 0, 8, 8)])
-def test_kpconv_random_shapes_vs_oracle(cuda, nq, ns, H, cin, cout):
+                                              (129, 257, 19, 130, 17), (64, 64, 48, 256, 128), (5, 9, 0, 8, 8),
+                                              (200, 300, 35, 32, 32), (90, 120, 42, 64, 64), (70, 80, 9, 128, 16),
+                                              (33, 40, 70, 12, 20), (10, 1, 5, 8, 8)])
+def test_kpconv_random_shapes_vs_oracle(cuda, kp_impl, nq, ns, H, cin, cout):
     """Ragged shapes, shadow indices, strided index rows; CUDA vs the torch-CPU restatement."""
     from oracle import model_ref
     from d3feat.pytorch_b200.blocks import _KPConvFunction
