@@ -389,15 +389,37 @@ def run_b200(args):
         tot_ms += avg_ms * calls_per_step
     per_layer.sort(key=lambda d: -d["logical_MB"])
     dom = per_layer[0]
+    # the gather kernel of that layer alone (events recorded inside d3f_kpconv_forward around kp2_correlate): it reads
+    # the neighbour rows / positions / indices and writes wf [Nq, K*Cin] for the contraction
+    gather = None
+    gk = [(k, v) for k, v in prof.items() if k[0] == "kpconv_gather" and k[1:6] == (dom["nq"], dom["ns"], dom["H"], dom["cin"], dom["cout"])]
+    if gk:
+        evs = gk[0][1]
+        g_ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+        g_bytes = dom["nq"] * dom["H"] * (4 * dom["cin"] + 16) + 12 * dom["nq"] + 4 * dom["nq"] * 15 * dom["cin"]
+        gather = {"kernel": "kp2_correlate (gather + kernel-point correlation)", "avg_ms_per_launch": g_ms,
+                  "algorithmic_bytes_per_launch": g_bytes, "GBps": g_bytes / g_ms / 1e6,
+                  "frac_of_hbm_peak": g_bytes / g_ms / 1e6 / pk["hbm_gbs"],
+                  "note": "bytes = Nq*H*(4Cin+12+4) + 12Nq read + 4*Nq*K*Cin written (wf)"}
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+        except Exception:
+            pass
     stage_ms = {}
     for k, evs in prof.items():
         stage_ms[k[0]] = stage_ms.get(k[0], 0.0) + sum(a.elapsed_time(b) for a, b in evs) / args.steps
     op_breakdown = sorted(([list(map(str, k)), len(evs) / args.steps, sum(a.elapsed_time(b) for a, b in evs) / args.steps]
                            for k, evs in prof.items()), key=lambda t: -t[2])[:40]
     roofline = {"bound": "hbm", "achieved": dom["GBps"], "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": dom["GBps"] / pk["hbm_gbs"], "traffic": None,
-                "kernel": "KPConv forward op (kp_rowpos + kp_correlate + kp_gemm) of the layer with the most algorithmic "
-                          "bytes: Nq=%d Ns=%d H=%d Cin=%d Cout=%d" % (dom["nq"], dom["ns"], dom["H"], dom["cin"], dom["cout"]),
+                "frac": dom["GBps"] / pk["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": "KPConv forward op (kp_rowpos + kp2_correlate gather + tcgen05 contraction) of the layer with the "
+                          "most algorithmic bytes: Nq=%d Ns=%d H=%d Cin=%d Cout=%d; achieved = SURVEY 8(d) logical gather "
+                          "bytes / CUDA-event time of the whole op" % (dom["nq"], dom["ns"], dom["H"], dom["cin"], dom["cout"]),
+                "gather_kernel": gather, "kpconv_impl": int(lib.d3f_get_kpconv_impl()),
                 "algorithmic_bytes_per_launch": dom["logical_MB"] * 1e6, "avg_ms_per_launch": dom["ms"],
                 "peak_source": pk_src + ", burst copy bandwidth",
                 "all_kpconv_fwd": {"logical_GB_per_step": tot_bytes / 1e9, "ms_per_step": tot_ms,

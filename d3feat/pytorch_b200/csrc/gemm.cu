@@ -230,10 +230,12 @@ __global__ void gemm_reduce_kernel(const float* __restrict__ part, int splits, i
     C[(size_t)m * ldc + n] = v;
 }
 
-// deterministic split: a function of K only (so the summation order of a row never depends on M)
-constexpr int DET_ROWS_MAX = 4096;   // above this many rows the output grid alone fills the chip: no split
+// deterministic split: a function of K only (so the summation order of a row never depends on M, i.e. on how many
+// capacity-padding rows the static pipeline adds).  Round 1c (ncu): the L1 contraction [13312 x 960] x [960 x 64] ran
+// as 104 CTAs x 30 serial K tiles (89 us) because large-M problems were never split; every K >= 512 problem is split
+// now, which also covers the small-M / large-K unary GEMMs of the deep levels (16-44 tiles on 148 SMs otherwise).
 constexpr int DET_KPS = 256;
-inline int det_splits(int M, int K) { return (M <= DET_ROWS_MAX && K >= 2 * DET_KPS) ? d3f_ceil_div(K, DET_KPS) : 1; }
+inline int det_splits(int M, int K) { (void)M; return K >= 2 * DET_KPS ? d3f_ceil_div(K, DET_KPS) : 1; }
 
 }  // namespace
 
@@ -271,8 +273,8 @@ int d3f_gemm_launch(const D3fGemm& in, bool ta, bool tb, cudaStream_t stream, fl
             g.partial = det_ws;
         }
     } else {
-        if (g.K > 0 && plain && tiles < 148) {
-            splits = min(d3f_ceil_div(296, tiles), d3f_ceil_div(g.K, 4 * BK));
+        if (g.K > 0 && plain && tiles < 296) {   // atomically combined partials: >= 2 K tiles per split, ~4 CTAs per SM
+            splits = min(d3f_ceil_div(592, tiles), d3f_ceil_div(g.K, 2 * BK));
             if (splits < 1) splits = 1;
         }
         kps = d3f_ceil_div(d3f_ceil_div(g.K > 0 ? g.K : 1, splits), BK) * BK;
@@ -315,7 +317,24 @@ int d3f_gemm_launch(const D3fGemm& in, bool ta, bool tb, cudaStream_t stream, fl
     return D3F_OK;
 }
 
-// C ABI: generic entry used by the fused UnaryBlock (blocks.py) and by tests.
+// C ABI: generic entries used by the fused UnaryBlock (blocks.py) and by tests.
+extern "C" size_t d3f_gemm_workspace_bytes(int M, int N, int K) { return d3f_gemm_det_workspace_bytes(M, N, K); }
+
+extern "C" int d3f_gemm_ex(int trans_a, int trans_b, int M, int N, int K, const float* A, int lda, const float* B,
+                           int ldb, float* C, int ldc, const float* row_scale, const float* k_scale,
+                           const float* bias, int leaky_relu, float slope, void* workspace, size_t workspace_bytes,
+                           d3f_stream stream) {
+    D3F_REQUIRE(M >= 0 && N >= 0 && K >= 0, D3F_ERR_INVALID, "bad sizes");
+    if (M == 0 || N == 0) return D3F_OK;
+    D3F_REQUIRE(C && (K == 0 || (A && B)), D3F_ERR_INVALID, "null pointer");
+    D3F_REQUIRE(!(k_scale && trans_b), D3F_ERR_UNSUPPORTED, "k_scale is applied on B[k][n] loads only");
+    const size_t need = d3f_gemm_det_workspace_bytes(M, N, K);
+    D3F_REQUIRE(need == 0 || (workspace && workspace_bytes >= need), D3F_ERR_WORKSPACE, "workspace too small");
+    D3fGemm g{M, N, K, A, lda, B, ldb, C, ldc, row_scale, k_scale, bias, leaky_relu, slope, 0, nullptr};
+    float dummy;
+    return d3f_gemm_launch(g, trans_a != 0, trans_b != 0, (cudaStream_t)stream, need ? (float*)workspace : &dummy, need);
+}
+
 extern "C" int d3f_gemm(int trans_a, int trans_b, int M, int N, int K, const float* A, int lda, const float* B,
                         int ldb, float* C, int ldc, const float* row_scale, const float* k_scale,
                         const float* bias, int leaky_relu, float slope, d3f_stream stream) {

@@ -518,6 +518,14 @@ static int kp_impl() {
 }
 extern "C" int d3f_get_kpconv_impl(void) { return kp_impl(); }
 
+// Optional CUDA events recorded immediately before / after the forward gather kernel (kp_correlate / kp2_correlate) on
+// the caller's stream, so a benchmark can time that kernel alone inside d3f_kpconv_forward.  NULL switches it off.
+static cudaEvent_t g_kp_ev0 = nullptr, g_kp_ev1 = nullptr;
+extern "C" void d3f_kpconv_set_gather_events(void* start_event, void* stop_event) {
+    g_kp_ev0 = (cudaEvent_t)start_event;
+    g_kp_ev1 = (cudaEvent_t)stop_event;
+}
+
 extern "C" size_t d3f_kpconv_workspace_bytes(int n_queries, int n_supports, int n_neighbors, int K, int c_in,
                                              int c_out) {
     (void)n_neighbors;
@@ -548,6 +556,7 @@ extern "C" int d3f_kpconv_forward(const float* q_pts, const float* s_pts, const 
     }
     KpArgs a{q_pts, s_pts, inds, (long long)ld_inds, x, kernel_points, modulations, w.rowpos,
              nq, ns, H, K, cin, kp_extent, influence, aggregation};
+    if (g_kp_ev0) D3F_CHECK_CUDA(cudaEventRecord(g_kp_ev0, stream));
     if (kp_impl() >= 1 && kp2_supported(H, ns, cin)) {
         Kp2Args a2{q_pts, s_pts, inds, (long long)ld_inds, x, kernel_points, modulations, w.rowpos,
                    nq, ns, H, K, cin, kp_extent, influence, aggregation, idx_is_64 ? 1 : 0, deformed ? 1 : 0};
@@ -560,6 +569,7 @@ extern "C" int d3f_kpconv_forward(const float* q_pts, const float* s_pts, const 
         KP_DISPATCH_ALL(kp_correlate_kernel, a, wf, wf_unmod, inv_n, deformed ? min_d2 : nullptr);
         D3F_CHECK_LAUNCH();
     }
+    if (g_kp_ev1) D3F_CHECK_CUDA(cudaEventRecord(g_kp_ev1, stream));
     D3fGemm g{nq, cout, K * cin, wf, K * cin, weights, cout, out, cout, inv_n, nullptr, nullptr, 0, 0.f, 0, nullptr};
     // forward: deterministic, padding-independent split-K (a 1e-7 perturbation here can flip a LeakyReLU mask)
     float dummy;

@@ -178,12 +178,20 @@ def kpconv_forward(q_pts, s_pts, inds, x, weights, kernel_points, extent, influe
     ws = _ws(lib.d3f_kpconv_workspace_bytes(nq, ns, H, K, cin, cout), dev)
     global launch_count
     launch_count += 1
+    gev = None
+    if PROFILE is not None:   # time the gather kernel alone as well (events recorded inside the C call)
+        gev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        gev[0].record(); gev[1].record()   # torch creates the cudaEvent_t lazily: record once to get the handles
+        lib.d3f_kpconv_set_gather_events(gev[0].cuda_event, gev[1].cuda_event)
+        PROFILE.setdefault(("kpconv_gather", nq, ns, H, cin, cout, bool(deformed)), []).append(gev)
     with _Timed(("kpconv_fwd", nq, ns, H, cin, cout, bool(deformed))):
       _lib.check(lib.d3f_kpconv_forward(_p(q_pts), _p(s_pts), _p(inds), 1 if inds.dtype == torch.int64 else 0,
                                       inds.stride(0) if H > 0 else 0, _p(x), _p(weights), _p(kernel_points),
                                       1 if deformed else 0, _p(modulations), nq, ns, H, K, cin, cout,
                                       float(extent), INFLUENCE[influence], AGGREGATION[aggregation],
                                       _p(out), _p(wf), _p(wf_un), _p(inv_n), _p(min_d2), _p(ws), ws.numel(), _stream()))
+    if gev is not None:
+        lib.d3f_kpconv_set_gather_events(None, None)
     return out, wf, wf_un, inv_n, min_d2
 
 
@@ -399,9 +407,10 @@ def detection_scores(feats, neighbors, eval_mode):
 
 
 # --------------------------------------------------------------------------- tensor-core GEMM (3xTF32) + fused linear
-def gemm(a, b, trans_a=False, trans_b=False, row_scale=None, k_scale=None, bias=None, slope=None):
+def gemm(a, b, trans_a=False, trans_b=False, row_scale=None, k_scale=None, bias=None, slope=None, deterministic=False):
     """C = act(row_scale * opA(a) @ (k_scale * opB(b)) + bias) via d3f_gemm (fp32-accurate tensor-core GEMM).
-    a: [M,K] (or [K,M] if trans_a); b: [K,N] (or [N,K] if trans_b)."""
+    a: [M,K] (or [K,M] if trans_a); b: [K,N] (or [N,K] if trans_b).  deterministic=True (forward pass): d3f_gemm_ex,
+    whose split-K depends on K only and sums its partials in a fixed order."""
     lib = _lib.load()
     a, b = _cuda_f32(a, "a"), _cuda_f32(b, "b")
     M, K = (a.shape[1], a.shape[0]) if trans_a else (a.shape[0], a.shape[1])
@@ -412,12 +421,17 @@ def gemm(a, b, trans_a=False, trans_b=False, row_scale=None, k_scale=None, bias=
     c = torch.empty((M, N), dtype=torch.float32, device=a.device)
     global launch_count
     launch_count += 1
+    args = (int(trans_a), int(trans_b), M, N, K, _p(a), a.stride(0), _p(b), b.stride(0), _p(c), N,
+            _p(None if row_scale is None else _cuda_f32(row_scale, "row_scale")),
+            _p(None if k_scale is None else _cuda_f32(k_scale, "k_scale")),
+            _p(None if bias is None else _cuda_f32(bias, "bias")),
+            0 if slope is None else 1, 0.0 if slope is None else float(slope))
     with _Timed(("gemm", M, N, K, bool(trans_a), bool(trans_b))):
-        _lib.check(lib.d3f_gemm(int(trans_a), int(trans_b), M, N, K, _p(a), a.stride(0), _p(b), b.stride(0), _p(c), N,
-                                _p(None if row_scale is None else _cuda_f32(row_scale, "row_scale")),
-                                _p(None if k_scale is None else _cuda_f32(k_scale, "k_scale")),
-                                _p(None if bias is None else _cuda_f32(bias, "bias")),
-                                0 if slope is None else 1, 0.0 if slope is None else float(slope), _stream()))
+        if deterministic:
+            ws = _ws(lib.d3f_gemm_workspace_bytes(M, N, K), a.device)
+            _lib.check(lib.d3f_gemm_ex(*args, _p(ws), ws.numel(), _stream()))
+        else:
+            _lib.check(lib.d3f_gemm(*args, _stream()))
     return c
 
 
@@ -436,7 +450,7 @@ class _FusedLinear(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, slope):
-        y = gemm(x, weight, trans_b=True, bias=bias, slope=slope)
+        y = gemm(x, weight, trans_b=True, bias=bias, slope=slope, deterministic=True)
         ctx.save_for_backward(x, weight, y if slope is not None else None)
         ctx.slope = slope
         return y

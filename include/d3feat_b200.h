@@ -125,6 +125,9 @@ int d3f_kpconv_forward(const float* q_pts, const float* s_pts, const void* inds,
  * exists for A/B measurements and parity tests. */
 void d3f_set_kpconv_impl(int impl);
 int d3f_get_kpconv_impl(void);
+/* Measurement hook: cudaEvent_t handles (or NULL, NULL) recorded on the caller's stream right before and right after
+ * the forward gather kernel of the next d3f_kpconv_forward calls, so that kernel can be timed alone. */
+void d3f_kpconv_set_gather_events(void* start_event, void* stop_event);
 
 /* backward: grad_out [Nq,Cout] ->
  *   grad_x [Ns,Cin] or NULL (fully overwritten), grad_weights [K,Cin,Cout] or NULL (overwritten),
@@ -222,6 +225,14 @@ int d3f_gemm_tcgen05_failed(void);
 int d3f_gemm(int trans_a, int trans_b, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
              float* C, int ldc, const float* row_scale, const float* k_scale, const float* bias,
              int leaky_relu, float slope, d3f_stream stream);
+/* Deterministic variant (the forward pass): long-K problems are split along K by a rule that depends on K only, the
+ * partial tiles go to `workspace` (d3f_gemm_workspace_bytes(M, N, K) bytes, 0 when no split is needed) and are summed
+ * in split order before row scale / bias / activation, so a row of C is bit-identical run to run and independent
+ * of M.  d3f_gemm instead combines split-K partials with float atomics and never splits a GEMM that has an epilogue. */
+size_t d3f_gemm_workspace_bytes(int M, int N, int K);
+int d3f_gemm_ex(int trans_a, int trans_b, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                float* C, int ldc, const float* row_scale, const float* k_scale, const float* bias,
+                int leaky_relu, float slope, void* workspace, size_t workspace_bytes, d3f_stream stream);
 
 #ifdef __cplusplus
 }

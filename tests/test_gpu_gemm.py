@@ -68,3 +68,21 @@ def test_fused_linear_autograd(cuda, gemm_impl):
         assert rel_err(out.detach().cpu(), y.detach()) < 2e-6
         assert rel_err(xg.grad.cpu(), xr.grad) < 2e-6 and rel_err(wg.grad.cpu(), wr.grad) < 5e-6
         assert rel_err(bg.grad.cpu(), br.grad) < 2e-6
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 512, 2048), (693, 1024, 3072), (13312, 64, 960), (100, 40, 511), (100, 40, 512)])
+def test_gemm_deterministic_split_with_epilogue(cuda, gemm_impl, M, N, K):
+    """d3f_gemm_ex: K-only split rule + ordered partial sums; bias / LeakyReLU applied after the reduction, and a
+    row's bits do not depend on how many rows the problem has (static-capacity padding)."""
+    from d3feat.pytorch_b200 import ops
+    rng = np.random.default_rng(M + N + K)
+    X = torch.from_numpy(rng.standard_normal((M, K)).astype(np.float32)).to(cuda)
+    W = torch.from_numpy((rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)).to(cuda)
+    b = torch.from_numpy(rng.standard_normal(N).astype(np.float32)).to(cuda)
+    ref = torch.nn.functional.leaky_relu(X.double() @ W.double().t() + b.double(), 0.1)
+    got = ops.gemm(X, W, trans_b=True, bias=b, slope=0.1, deterministic=True)
+    assert rel_err(got.cpu(), ref.cpu()) < 2e-6 * max(1.0, np.sqrt(K) / 8)
+    again = ops.gemm(X, W, trans_b=True, bias=b, slope=0.1, deterministic=True)
+    assert torch.equal(got, again)
+    part = ops.gemm(X[: M // 2 + 1].contiguous(), W, trans_b=True, bias=b, slope=0.1, deterministic=True)
+    assert torch.equal(got[: M // 2 + 1], part)

@@ -28,6 +28,11 @@ st = PairStep(model, cfg, limits, plan_capacities(sizes), n, n, PairLoss("circle
 st(pairs[0]); st.capture()
 for i in range(3): st(pairs[i % 2])
 torch.cuda.synchronize()
+if os.environ.get("D3F_NCU"):   # under `ncu --profile-from-start off`: exactly one replay of the graph step is profiled
+    torch.cuda.profiler.start()
+    st(pairs[0]); torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+    sys.exit(0)
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for i in range(5): st(pairs[i % 2])
     torch.cuda.synchronize()
