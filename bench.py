@@ -241,7 +241,9 @@ def run_b200(args):
     model = KPFCNN(cfg).to(dev)
     model.train()
     opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.98, weight_decay=1e-6)  # config.py:62-69
-    flat = parallel.FlatGradients(model)   # all gradients are views of one buffer: zero() / one all-reduce
+    # multi-GPU: all gradients are views of one buffer (zero() + ONE all-reduce); single GPU: plain per-parameter
+    # gradients created by the backward pass (saves one accumulate kernel per parameter, ~130 launches per step)
+    flat = parallel.FlatGradients(model) if world > 1 else None
     loss_fn = PairLoss("circle", "euclidean", cfg.log_scale, cfg.safe_radius, cfg.pos_margin, cfg.neg_margin)
 
     pairs = make_pairs(args.points, POOL, 100 * rank)
@@ -282,10 +284,14 @@ def run_b200(args):
         loss = out["desc_loss"] * cfg.desc_loss_weight + out["det_loss"] * cfg.det_loss_weight
         t0 = tick("loss", t0)
         if not args.fwd_only:
-            flat.zero()
+            if flat is not None:
+                flat.zero()
+            else:
+                opt.zero_grad(set_to_none=True)
             loss.backward()
             t0 = tick("backward", t0)
-            flat.allreduce()
+            if flat is not None:
+                flat.allreduce()
             opt.step()
             t0 = tick("optimizer", t0)
         return float(loss.detach()) if read_loss else loss

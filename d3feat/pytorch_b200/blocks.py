@@ -44,16 +44,18 @@ def global_average(x, batch_lengths):
 
 # ----------------------------------------------------------------------------- KPConv
 class _KPConvFunction(torch.autograd.Function):
-    """out = KPConv(q, s, inds, x; W, kernel points [, modulations]) through libd3feat_b200."""
+    """out = act(KPConv(q, s, inds, x; W, kernel points [, modulations]) + bias) through libd3feat_b200
+    (bias / slope None: the bare convolution)."""
 
     @staticmethod
     def forward(ctx, q_pts, s_pts, inds, x, weights, kpoints, modulations, extent, influence, aggregation,
-                deformed, want_min_d2):
+                deformed, want_min_d2, bias=None, slope=None):
         out, wf, wf_un, inv_n, min_d2 = ops.kpconv_forward(q_pts, s_pts, inds, x, weights, kpoints, extent,
                                                            influence, aggregation, deformed, modulations,
-                                                           want_min_d2)
-        ctx.save_for_backward(q_pts, s_pts, inds, x, weights, kpoints, modulations, wf, wf_un, inv_n)
-        ctx.cfg = (extent, influence, aggregation, deformed)
+                                                           want_min_d2, bias, slope)
+        ctx.save_for_backward(q_pts, s_pts, inds, x, weights, kpoints, modulations, wf, wf_un, inv_n,
+                              out if slope is not None else None)
+        ctx.cfg = (extent, influence, aggregation, deformed, slope)
         if min_d2 is None:
             min_d2 = out.new_empty(0)
         ctx.mark_non_differentiable(min_d2)
@@ -61,16 +63,19 @@ class _KPConvFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out, _grad_min_d2):
-        q_pts, s_pts, inds, x, weights, kpoints, modulations, wf, wf_un, inv_n = ctx.saved_tensors
-        extent, influence, aggregation, deformed = ctx.cfg
+        q_pts, s_pts, inds, x, weights, kpoints, modulations, wf, wf_un, inv_n, out = ctx.saved_tensors
+        extent, influence, aggregation, deformed, slope = ctx.cfg
         need = ctx.needs_input_grad
+        if slope is not None:   # out = leaky(z) has the sign of z: the mask comes from the saved output
+            grad_out = torch.ops.aten.leaky_relu_backward(grad_out.contiguous(), out, float(slope), True)
+        gbias = ops.colsum(grad_out) if (len(need) > 12 and need[12]) else None
         gx, gw, gkp, gmod = ops.kpconv_backward(
             q_pts.float().contiguous(), s_pts.float().contiguous(),
             inds if inds.dtype in (torch.int32, torch.int64) else inds.long(),
             x.float().contiguous(), weights.contiguous(), kpoints.float().contiguous(), extent, influence,
             aggregation, deformed, modulations, wf, wf_un, inv_n, grad_out,
             need_x=need[3], need_w=need[4], need_kp=need[5] and deformed, need_mod=need[6])
-        return None, None, None, gx, gw, gkp, gmod, None, None, None, None, None
+        return (None, None, None, gx, gw, gkp, gmod, None, None, None, None, None, gbias, None)[:len(need)]
 
 
 class KPConv(nn.Module):
@@ -124,11 +129,13 @@ class KPConv(nn.Module):
         kp = load_kernels(self.radius, self.K, dimension=self.p_dim, fixed=self.fixed_kernel_points)
         return Parameter(torch.tensor(kp, dtype=torch.float32), requires_grad=False)
 
-    def forward(self, q_pts, s_pts, neighb_inds, x):
+    def forward(self, q_pts, s_pts, neighb_inds, x, bias=None, slope=None):
+        """Reference signature forward(q_pts, s_pts, neighb_inds, x).  The optional `bias` [out_channels] and `slope`
+        fuse the `+ bias` / LeakyReLU(slope) that the calling block applies next into the contraction's epilogue."""
         kpoints, modulations, deformed = self.kernel_points, None, False
         if self.deformable:
             # offsets come from a rigid KPConv over the same neighbourhoods (blocks.py:243-266)
-            self.offset_features = self.offset_conv(q_pts, s_pts, neighb_inds, x) + self.offset_bias
+            self.offset_features = self.offset_conv(q_pts, s_pts, neighb_inds, x, bias=self.offset_bias)
             n_off = self.p_dim * self.K
             unscaled = self.offset_features[:, :n_off].reshape(-1, self.K, self.p_dim)
             if self.modulated:
@@ -137,7 +144,7 @@ class KPConv(nn.Module):
             kpoints, deformed = self.deformed_KP, True
         out, min_d2 = _KPConvFunction.apply(q_pts, s_pts, neighb_inds, x, self.weights, kpoints, modulations,
                                             float(self.KP_extent), self.KP_influence, self.aggregation_mode,
-                                            deformed, deformed)
+                                            deformed, deformed, bias, slope)
         if deformed:
             self.min_d2 = min_d2
         return out
@@ -192,11 +199,15 @@ class UnaryBlock(nn.Module):
 
     def forward(self, x, batch=None):
         if not self.use_bn and x.is_cuda:
-            # Linear + learned bias (+ LeakyReLU 0.1) as one tensor-core GEMM with a fused epilogue
-            return ops.fused_linear(x, self.mlp.weight, self.mlp.bias + self.batch_norm.bias,
-                                    None if self.no_relu else 0.1)
+            # Linear + both biases (+ LeakyReLU 0.1) as one tensor-core GEMM with a fused epilogue
+            return ops.fused_linear(x, self.mlp.weight, self.mlp.bias, None if self.no_relu else 0.1,
+                                    bias2=self.batch_norm.bias)
         x = self.batch_norm(self.mlp(x))
         return x if self.no_relu else self.leaky_relu(x)
+
+    def forward_residual(self, x, residual, slope):
+        """leaky_relu(self(x) + residual, slope) for a no_relu block without batch norm, as one GEMM."""
+        return ops.fused_linear(x, self.mlp.weight, self.mlp.bias, slope, bias2=self.batch_norm.bias, residual=residual)
 
     def __repr__(self):
         return 'UnaryBlock(in_feat: {:d}, out_feat: {:d}, BN: {:s}, ReLU: {:s})'.format(
@@ -254,6 +265,8 @@ class SimpleBlock(nn.Module):
 
     def forward(self, x, batch):
         q_pts, s_pts, inds = _conv_geometry(self.block_name, self.layer_ind, batch)
+        if not self.use_bn and x.is_cuda:   # bias + LeakyReLU in the contraction's epilogue
+            return self.KPConv(q_pts, s_pts, inds, x, bias=self.batch_norm.bias, slope=0.1)
         return self.leaky_relu(self.batch_norm(self.KPConv(q_pts, s_pts, inds, x)))
 
 
@@ -279,9 +292,13 @@ class ResnetBottleneckBlock(nn.Module):
 
     def forward(self, features, batch):
         q_pts, s_pts, inds = _conv_geometry(self.block_name, self.layer_ind, batch)
+        shortcut = max_pool(features, inds) if 'strided' in self.block_name else features
+        if not self.use_bn and features.is_cuda:
+            # conv + bias + LeakyReLU in one op; unary2 + shortcut add + LeakyReLU in one GEMM epilogue
+            x = self.KPConv(q_pts, s_pts, inds, self.unary1(features), bias=self.batch_norm_conv.bias, slope=0.1)
+            return self.unary2.forward_residual(x, self.unary_shortcut(shortcut), 0.1)
         x = self.KPConv(q_pts, s_pts, inds, self.unary1(features))
         x = self.unary2(self.leaky_relu(self.batch_norm_conv(x)))
-        shortcut = max_pool(features, inds) if 'strided' in self.block_name else features
         return self.leaky_relu(x + self.unary_shortcut(shortcut))
 
 

@@ -210,6 +210,8 @@ tc_gemm_kernel(D3fGemm g) {
                     float* dst = g.C + (size_t)m * g.ldc + n;
                     if (atomic) { atomicAdd(dst, v); continue; }
                     if (g.bias) v += g.bias[n];
+                    if (g.bias2) v += g.bias2[n];
+                    if (g.res) v += g.res[(size_t)m * g.ldr + n];
                     if (g.act) v = v > 0.f ? v : v * g.slope;
                     *dst = v;
                 }
@@ -218,7 +220,7 @@ tc_gemm_kernel(D3fGemm g) {
 
 __global__ void gemm_reduce_kernel(const float* __restrict__ part, int splits, int M, int N, float* __restrict__ C,
                                    int ldc, const float* __restrict__ rs, const float* __restrict__ bias, int act,
-                                   float slope) {
+                                   float slope, const float* __restrict__ bias2, const float* __restrict__ res, int ldr) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)M * N) return;
     const int m = (int)(t / N), n = (int)(t % N);
@@ -226,6 +228,8 @@ __global__ void gemm_reduce_kernel(const float* __restrict__ part, int splits, i
     for (int z = 0; z < splits; ++z) v += part[(size_t)z * M * N + t];   // fixed order
     if (rs) v *= rs[m];
     if (bias) v += bias[n];
+    if (bias2) v += bias2[n];
+    if (res) v += res[(size_t)m * ldr + n];
     if (act) v = v > 0.f ? v : v * slope;
     C[(size_t)m * ldc + n] = v;
 }
@@ -263,7 +267,7 @@ int d3f_gemm_launch(const D3fGemm& in, bool ta, bool tb, cudaStream_t stream, fl
     if (g.M <= 0 || g.N <= 0) return D3F_OK;
     const int tiles = d3f_ceil_div(g.M, BM) * d3f_ceil_div(g.N, BN);
     int splits = 1, kps;
-    const bool plain = !g.bias && !g.act;   // atomically combined partials cannot take a non-linear epilogue
+    const bool plain = !g.bias && !g.act && !g.bias2 && !g.res;   // atomically combined partials cannot take an epilogue
     if (det_ws) {
         splits = det_splits(g.M, g.K);
         kps = splits > 1 ? DET_KPS : d3f_ceil_div(g.K > 0 ? g.K : 1, BK) * BK;
@@ -311,7 +315,7 @@ int d3f_gemm_launch(const D3fGemm& in, bool ta, bool tb, cudaStream_t stream, fl
     if (g.partial) {
         const size_t total = (size_t)g.M * g.N;
         gemm_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(g.partial, splits, g.M, g.N, g.C, g.ldc,
-                                                                              g.rs, g.bias, g.act, g.slope);
+                                                                              g.rs, g.bias, g.act, g.slope, g.bias2, g.res, g.ldr);
         D3F_CHECK_LAUNCH();
     }
     return D3F_OK;
@@ -322,15 +326,16 @@ extern "C" size_t d3f_gemm_workspace_bytes(int M, int N, int K) { return d3f_gem
 
 extern "C" int d3f_gemm_ex(int trans_a, int trans_b, int M, int N, int K, const float* A, int lda, const float* B,
                            int ldb, float* C, int ldc, const float* row_scale, const float* k_scale,
-                           const float* bias, int leaky_relu, float slope, void* workspace, size_t workspace_bytes,
-                           d3f_stream stream) {
+                           const float* bias, const float* bias2, const float* residual, int ld_residual,
+                           int leaky_relu, float slope, void* workspace, size_t workspace_bytes, d3f_stream stream) {
     D3F_REQUIRE(M >= 0 && N >= 0 && K >= 0, D3F_ERR_INVALID, "bad sizes");
     if (M == 0 || N == 0) return D3F_OK;
     D3F_REQUIRE(C && (K == 0 || (A && B)), D3F_ERR_INVALID, "null pointer");
     D3F_REQUIRE(!(k_scale && trans_b), D3F_ERR_UNSUPPORTED, "k_scale is applied on B[k][n] loads only");
     const size_t need = d3f_gemm_det_workspace_bytes(M, N, K);
     D3F_REQUIRE(need == 0 || (workspace && workspace_bytes >= need), D3F_ERR_WORKSPACE, "workspace too small");
-    D3fGemm g{M, N, K, A, lda, B, ldb, C, ldc, row_scale, k_scale, bias, leaky_relu, slope, 0, nullptr};
+    D3fGemm g{M, N, K, A, lda, B, ldb, C, ldc, row_scale, k_scale, bias, leaky_relu, slope, 0, nullptr,
+              bias2, residual, ld_residual};
     float dummy;
     return d3f_gemm_launch(g, trans_a != 0, trans_b != 0, (cudaStream_t)stream, need ? (float*)workspace : &dummy, need);
 }

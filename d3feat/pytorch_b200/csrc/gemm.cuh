@@ -14,9 +14,12 @@ struct D3fGemm {
     float slope;
     int k_per_split;     // filled by the launcher
     float* partial;      // filled by the launcher: deterministic split-K partials [splits][M][N], or null
+    const float* bias2;  // optional second bias [N] (UnaryBlock: Linear bias + the learned bias that replaces batch norm)
+    const float* res;    // optional residual [M, ldr] added before the activation (ResnetBottleneckBlock shortcut)
+    int ldr;
 };
 
-// C[M,N] = act(rs[m] * sum_k opA(m,k) * ks[k] * opB(k,n) + bias[n]);  ta: A stored [K,M];  tb: B stored [N,K]
+// C[M,N] = act(rs[m] * sum_k opA(m,k) * ks[k] * opB(k,n) + bias[n] + bias2[n] + res[m,n]);  ta: A stored [K,M];  tb: B stored [N,K]
 // `det_ws` != null selects the DETERMINISTIC split-K used by the forward pass: the split size depends on K
 // only (never on M), partial tiles go to det_ws and are summed in split order by a second kernel, so a row of C
 // is bit-identical run to run and independent of how many (padding) rows M has.  Without it, split-K partials

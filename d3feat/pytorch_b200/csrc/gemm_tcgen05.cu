@@ -271,7 +271,11 @@ tc5_gemm_kernel(D3fGemm g) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 float y = xs[e] * sc;
-                if (g.bias && n + e < g.N) y += g.bias[n + e];
+                if (n + e < g.N) {
+                    if (g.bias) y += g.bias[n + e];
+                    if (g.bias2) y += g.bias2[n + e];
+                    if (g.res) y += g.res[(size_t)row * g.ldr + n + e];
+                }
                 if (g.act) y = y > 0.f ? y : y * g.slope;
                 xs[e] = y;
             }

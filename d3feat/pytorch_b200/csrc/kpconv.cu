@@ -533,12 +533,34 @@ extern "C" size_t d3f_kpconv_workspace_bytes(int n_queries, int n_supports, int 
     return kp_layout(&w, nullptr, 0, n_queries, n_supports, K, c_in, c_out);
 }
 
+extern "C" int d3f_kpconv_forward_ex(const float* q_pts, const float* s_pts, const void* inds, int idx_is_64,
+                                     int64_t ld_inds, const float* x, const float* weights,
+                                     const float* kernel_points, int deformed, const float* modulations,
+                                     int nq, int ns, int H, int K, int cin, int cout, float kp_extent, int influence,
+                                     int aggregation, const float* bias, int leaky_relu, float slope,
+                                     float* out, float* wf, float* wf_unmod, float* inv_n,
+                                     float* min_d2, void* workspace, size_t workspace_bytes, d3f_stream stream_);
+
 extern "C" int d3f_kpconv_forward(const float* q_pts, const float* s_pts, const void* inds, int idx_is_64,
                                   int64_t ld_inds, const float* x, const float* weights,
                                   const float* kernel_points, int deformed, const float* modulations,
                                   int nq, int ns, int H, int K, int cin, int cout, float kp_extent, int influence,
                                   int aggregation, float* out, float* wf, float* wf_unmod, float* inv_n,
                                   float* min_d2, void* workspace, size_t workspace_bytes, d3f_stream stream_) {
+    return d3f_kpconv_forward_ex(q_pts, s_pts, inds, idx_is_64, ld_inds, x, weights, kernel_points, deformed, modulations,
+                                 nq, ns, H, K, cin, cout, kp_extent, influence, aggregation, nullptr, 0, 0.f,
+                                 out, wf, wf_unmod, inv_n, min_d2, workspace, workspace_bytes, stream_);
+}
+
+// out = act(diag(1/n) wf W + bias): the learned bias that replaces batch norm and the LeakyReLU of SimpleBlock /
+// ResnetBottleneckBlock (blocks.py:597, :671) ride in the contraction's epilogue.
+extern "C" int d3f_kpconv_forward_ex(const float* q_pts, const float* s_pts, const void* inds, int idx_is_64,
+                                     int64_t ld_inds, const float* x, const float* weights,
+                                     const float* kernel_points, int deformed, const float* modulations,
+                                     int nq, int ns, int H, int K, int cin, int cout, float kp_extent, int influence,
+                                     int aggregation, const float* bias, int leaky_relu, float slope,
+                                     float* out, float* wf, float* wf_unmod, float* inv_n,
+                                     float* min_d2, void* workspace, size_t workspace_bytes, d3f_stream stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc = kp_check(nq, ns, H, K, cin, cout);
     if (rc) return rc;
@@ -570,7 +592,7 @@ extern "C" int d3f_kpconv_forward(const float* q_pts, const float* s_pts, const 
         D3F_CHECK_LAUNCH();
     }
     if (g_kp_ev1) D3F_CHECK_CUDA(cudaEventRecord(g_kp_ev1, stream));
-    D3fGemm g{nq, cout, K * cin, wf, K * cin, weights, cout, out, cout, inv_n, nullptr, nullptr, 0, 0.f, 0, nullptr};
+    D3fGemm g{nq, cout, K * cin, wf, K * cin, weights, cout, out, cout, inv_n, nullptr, bias, leaky_relu, slope, 0, nullptr};
     // forward: deterministic, padding-independent split-K (a 1e-7 perturbation here can flip a LeakyReLU mask)
     float dummy;
     return d3f_gemm_launch(g, false, false, stream, w.det_bytes ? w.det : &dummy, w.det_bytes);

@@ -187,7 +187,9 @@ class PairStep:
             if self.flat is not None:
                 self.flat.zero()
             else:
-                self.optimizer.zero_grad(set_to_none=False)
+                # gradients are (re)created by the backward pass: no zero-fill and no accumulate kernel per parameter
+                # (inside a CUDA graph they come from the graph's private pool at the same addresses every replay)
+                self.optimizer.zero_grad(set_to_none=True)
             loss.backward()
             if self.flat is not None:
                 self.flat.allreduce(self.group)

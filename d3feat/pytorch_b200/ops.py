@@ -153,7 +153,8 @@ def grid_subsample_raw(points, lengths, sample_dl, out_capacity):
 
 # --------------------------------------------------------------------------- KPConv
 def kpconv_forward(q_pts, s_pts, inds, x, weights, kernel_points, extent, influence, aggregation,
-                   deformed=False, modulations=None, want_min_d2=False):
+                   deformed=False, modulations=None, want_min_d2=False, bias=None, slope=None):
+    """d3f_kpconv_forward_ex: out = act(KPConv(...) + bias) with act = LeakyReLU(slope) when slope is given."""
     lib = _lib.load()
     q_pts, s_pts, x = _cuda_f32(q_pts, "q_pts"), _cuda_f32(s_pts, "s_pts"), _cuda_f32(x, "x")
     weights, kernel_points = _cuda_f32(weights, "weights"), _cuda_f32(kernel_points, "kernel_points")
@@ -175,6 +176,10 @@ def kpconv_forward(q_pts, s_pts, inds, x, weights, kernel_points, extent, influe
     min_d2 = torch.empty((nq, K), dtype=torch.float32, device=dev) if (deformed and want_min_d2) else None
     if modulations is not None:
         modulations = _cuda_f32(modulations, "modulations")
+    if bias is not None:
+        bias = _cuda_f32(bias, "bias")
+        if bias.numel() != cout:
+            raise RuntimeError("KPConv: bias must have out_channels = %d elements" % cout)
     ws = _ws(lib.d3f_kpconv_workspace_bytes(nq, ns, H, K, cin, cout), dev)
     global launch_count
     launch_count += 1
@@ -185,11 +190,12 @@ def kpconv_forward(q_pts, s_pts, inds, x, weights, kernel_points, extent, influe
         lib.d3f_kpconv_set_gather_events(gev[0].cuda_event, gev[1].cuda_event)
         PROFILE.setdefault(("kpconv_gather", nq, ns, H, cin, cout, bool(deformed)), []).append(gev)
     with _Timed(("kpconv_fwd", nq, ns, H, cin, cout, bool(deformed))):
-      _lib.check(lib.d3f_kpconv_forward(_p(q_pts), _p(s_pts), _p(inds), 1 if inds.dtype == torch.int64 else 0,
-                                      inds.stride(0) if H > 0 else 0, _p(x), _p(weights), _p(kernel_points),
-                                      1 if deformed else 0, _p(modulations), nq, ns, H, K, cin, cout,
-                                      float(extent), INFLUENCE[influence], AGGREGATION[aggregation],
-                                      _p(out), _p(wf), _p(wf_un), _p(inv_n), _p(min_d2), _p(ws), ws.numel(), _stream()))
+      _lib.check(lib.d3f_kpconv_forward_ex(_p(q_pts), _p(s_pts), _p(inds), 1 if inds.dtype == torch.int64 else 0,
+                                         inds.stride(0) if H > 0 else 0, _p(x), _p(weights), _p(kernel_points),
+                                         1 if deformed else 0, _p(modulations), nq, ns, H, K, cin, cout,
+                                         float(extent), INFLUENCE[influence], AGGREGATION[aggregation],
+                                         _p(bias), 0 if slope is None else 1, 0.0 if slope is None else float(slope),
+                                         _p(out), _p(wf), _p(wf_un), _p(inv_n), _p(min_d2), _p(ws), ws.numel(), _stream()))
     if gev is not None:
         lib.d3f_kpconv_set_gather_events(None, None)
     return out, wf, wf_un, inv_n, min_d2
@@ -407,10 +413,12 @@ def detection_scores(feats, neighbors, eval_mode):
 
 
 # --------------------------------------------------------------------------- tensor-core GEMM (3xTF32) + fused linear
-def gemm(a, b, trans_a=False, trans_b=False, row_scale=None, k_scale=None, bias=None, slope=None, deterministic=False):
-    """C = act(row_scale * opA(a) @ (k_scale * opB(b)) + bias) via d3f_gemm (fp32-accurate tensor-core GEMM).
-    a: [M,K] (or [K,M] if trans_a); b: [K,N] (or [N,K] if trans_b).  deterministic=True (forward pass): d3f_gemm_ex,
-    whose split-K depends on K only and sums its partials in a fixed order."""
+def gemm(a, b, trans_a=False, trans_b=False, row_scale=None, k_scale=None, bias=None, slope=None, deterministic=False,
+         bias2=None, residual=None):
+    """C = act(row_scale * opA(a) @ (k_scale * opB(b)) + bias + bias2 + residual) via d3f_gemm / d3f_gemm_ex
+    (fp32-accurate tensor-core GEMM).  a: [M,K] (or [K,M] if trans_a); b: [K,N] (or [N,K] if trans_b).
+    deterministic=True (forward pass): d3f_gemm_ex, whose split-K depends on K only and sums its partials in a fixed
+    order; bias2 / residual need it."""
     lib = _lib.load()
     a, b = _cuda_f32(a, "a"), _cuda_f32(b, "b")
     M, K = (a.shape[1], a.shape[0]) if trans_a else (a.shape[0], a.shape[1])
@@ -421,17 +429,22 @@ def gemm(a, b, trans_a=False, trans_b=False, row_scale=None, k_scale=None, bias=
     c = torch.empty((M, N), dtype=torch.float32, device=a.device)
     global launch_count
     launch_count += 1
-    args = (int(trans_a), int(trans_b), M, N, K, _p(a), a.stride(0), _p(b), b.stride(0), _p(c), N,
+    head = (int(trans_a), int(trans_b), M, N, K, _p(a), a.stride(0), _p(b), b.stride(0), _p(c), N,
             _p(None if row_scale is None else _cuda_f32(row_scale, "row_scale")),
             _p(None if k_scale is None else _cuda_f32(k_scale, "k_scale")),
-            _p(None if bias is None else _cuda_f32(bias, "bias")),
-            0 if slope is None else 1, 0.0 if slope is None else float(slope))
+            _p(None if bias is None else _cuda_f32(bias, "bias")))
+    act = (0 if slope is None else 1, 0.0 if slope is None else float(slope))
     with _Timed(("gemm", M, N, K, bool(trans_a), bool(trans_b))):
-        if deterministic:
+        if deterministic or bias2 is not None or residual is not None:
+            if residual is not None:
+                residual = _cuda_f32(residual, "residual")
+                if tuple(residual.shape) != (M, N):
+                    raise RuntimeError("gemm: residual must be [%d, %d]" % (M, N))
             ws = _ws(lib.d3f_gemm_workspace_bytes(M, N, K), a.device)
-            _lib.check(lib.d3f_gemm_ex(*args, _p(ws), ws.numel(), _stream()))
+            _lib.check(lib.d3f_gemm_ex(*head, _p(None if bias2 is None else _cuda_f32(bias2, "bias2")), _p(residual),
+                                       N, *act, _p(ws), ws.numel(), _stream()))
         else:
-            _lib.check(lib.d3f_gemm(*args, _stream()))
+            _lib.check(lib.d3f_gemm(*head, *act, _stream()))
     return c
 
 
@@ -445,12 +458,13 @@ def colsum(x):
 
 
 class _FusedLinear(torch.autograd.Function):
-    """y = LeakyReLU_slope(x @ W^T + b)  (slope None: no activation) -- the UnaryBlock body
-    (models/blocks.py:505-510 with use_bn=False) as one GEMM with a fused epilogue."""
+    """y = LeakyReLU_slope(x @ W^T + b + b2 + residual)  (slope None: no activation; b2 / residual optional) -- the
+    UnaryBlock body (models/blocks.py:505-510 with use_bn=False: Linear bias + learned bias) and, with `residual`, the
+    tail of ResnetBottleneckBlock (leaky_relu(unary2(x) + shortcut), blocks.py:686) as ONE GEMM with a fused epilogue."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, slope):
-        y = gemm(x, weight, trans_b=True, bias=bias, slope=slope, deterministic=True)
+    def forward(ctx, x, weight, bias, bias2, residual, slope):
+        y = gemm(x, weight, trans_b=True, bias=bias, slope=slope, deterministic=True, bias2=bias2, residual=residual)
         ctx.save_for_backward(x, weight, y if slope is not None else None)
         ctx.slope = slope
         return y
@@ -458,13 +472,15 @@ class _FusedLinear(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         x, weight, y = ctx.saved_tensors
-        dz = gy if y is None else gy * torch.where(y > 0, 1.0, float(ctx.slope))
+        # y = leaky(z) has the sign of z (slope > 0), so the mask can be taken from the saved output: one kernel
+        dz = gy if y is None else torch.ops.aten.leaky_relu_backward(gy, y, float(ctx.slope), True)
         dz = dz.contiguous()
-        dx = gemm(dz, weight) if ctx.needs_input_grad[0] else None                 # [M,out] @ [out,in]
-        dw = gemm(dz, x, trans_a=True) if ctx.needs_input_grad[1] else None         # dz^T [out,M] @ x [M,in]
-        db = colsum(dz) if ctx.needs_input_grad[2] else None
-        return dx, dw, db, None
+        need = ctx.needs_input_grad
+        dx = gemm(dz, weight) if need[0] else None                 # [M,out] @ [out,in]
+        dw = gemm(dz, x, trans_a=True) if need[1] else None         # dz^T [out,M] @ x [M,in]
+        db = colsum(dz) if (need[2] or need[3]) else None
+        return dx, dw, db if need[2] else None, db if need[3] else None, dz if need[4] else None, None
 
 
-def fused_linear(x, weight, bias, slope=None):
-    return _FusedLinear.apply(x, weight, bias, slope)
+def fused_linear(x, weight, bias, slope=None, bias2=None, residual=None):
+    return _FusedLinear.apply(x, weight, bias, bias2, residual, slope)

@@ -119,6 +119,19 @@ int d3f_kpconv_forward(const float* q_pts, const float* s_pts, const void* inds,
                        float* out, float* wf, float* wf_unmod, float* inv_n, float* min_d2,
                        void* workspace, size_t workspace_bytes, d3f_stream stream);
 
+/* Same as d3f_kpconv_forward with the block epilogue fused into the contraction:
+ *   out = act(conv + bias[Cout]),  act = LeakyReLU(slope) if leaky_relu != 0
+ * (SimpleBlock / ResnetBottleneckBlock apply `x + bias` (BatchNormBlock with use_bn = False) and LeakyReLU(0.1) right
+ * after the convolution, blocks.py:597, :671; the deformable offset head adds offset_bias, blocks.py:246). */
+int d3f_kpconv_forward_ex(const float* q_pts, const float* s_pts, const void* inds, int idx_is_64,
+                          int64_t ld_inds, const float* x, const float* weights,
+                          const float* kernel_points, int deformed, const float* modulations,
+                          int n_queries, int n_supports, int n_neighbors, int K, int c_in, int c_out,
+                          float kp_extent, int influence, int aggregation,
+                          const float* bias, int leaky_relu, float slope,
+                          float* out, float* wf, float* wf_unmod, float* inv_n, float* min_d2,
+                          void* workspace, size_t workspace_bytes, d3f_stream stream);
+
 /* Gather-kernel generation used by d3f_kpconv_forward/_backward: 0 = v1 (warp per query, lanes over neighbours),
  * 1 = v2 with FFMA accumulation, 2 = v2 with mma.sync 3xTF32 accumulation (csrc/kpconv2.cu); -1 restores the default
  * (environment D3F_KPCONV_IMPL = v1 | ffma | mma, else 2).  All three compute the same function; the selector
@@ -228,10 +241,13 @@ int d3f_gemm(int trans_a, int trans_b, int M, int N, int K, const float* A, int 
 /* Deterministic variant (the forward pass): long-K problems are split along K by a rule that depends on K only, the
  * partial tiles go to `workspace` (d3f_gemm_workspace_bytes(M, N, K) bytes, 0 when no split is needed) and are summed
  * in split order before row scale / bias / activation, so a row of C is bit-identical run to run and independent
- * of M.  d3f_gemm instead combines split-K partials with float atomics and never splits a GEMM that has an epilogue. */
+ * of M.  d3f_gemm instead combines split-K partials with float atomics and never splits a GEMM that has an epilogue.
+ * Extra epilogue terms: C = act(... + bias[n] + bias2[n] + residual[m, n]) (bias2 / residual may be NULL): the
+ * UnaryBlock's Linear bias + learned bias, and the ResnetBottleneckBlock shortcut add (blocks.py:505-510, :686). */
 size_t d3f_gemm_workspace_bytes(int M, int N, int K);
 int d3f_gemm_ex(int trans_a, int trans_b, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                 float* C, int ldc, const float* row_scale, const float* k_scale, const float* bias,
+                const float* bias2, const float* residual, int ld_residual,
                 int leaky_relu, float slope, void* workspace, size_t workspace_bytes, d3f_stream stream);
 
 #ifdef __cplusplus

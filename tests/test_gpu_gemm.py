@@ -86,3 +86,24 @@ def test_gemm_deterministic_split_with_epilogue(cuda, gemm_impl, M, N, K):
     assert torch.equal(got, again)
     part = ops.gemm(X[: M // 2 + 1].contiguous(), W, trans_b=True, bias=b, slope=0.1, deterministic=True)
     assert torch.equal(got[: M // 2 + 1], part)
+
+
+def test_fused_linear_two_biases_residual_autograd(cuda, gemm_impl):
+    """leaky(x W^T + b + b2 + residual): the ResnetBottleneckBlock tail as one GEMM (blocks.py:686)."""
+    from d3feat.pytorch_b200 import ops
+    rng = np.random.default_rng(5)
+    x = torch.from_numpy(rng.standard_normal((333, 64)).astype(np.float32))
+    w = torch.from_numpy((rng.standard_normal((256, 64)) / 8).astype(np.float32))
+    b = torch.from_numpy(rng.standard_normal(256).astype(np.float32))
+    b2 = torch.from_numpy(rng.standard_normal(256).astype(np.float32))
+    r = torch.from_numpy(rng.standard_normal((333, 256)).astype(np.float32))
+    g = torch.from_numpy(rng.standard_normal((333, 256)).astype(np.float32))
+    ref_in = [t.double().requires_grad_(True) for t in (x, w, b, b2, r)]
+    y = torch.nn.functional.leaky_relu(ref_in[0] @ ref_in[1].t() + ref_in[2] + ref_in[3] + ref_in[4], 0.1)
+    (y * g.double()).sum().backward()
+    gpu_in = [t.to(cuda).requires_grad_(True) for t in (x, w, b, b2, r)]
+    out = ops.fused_linear(gpu_in[0], gpu_in[1], gpu_in[2], 0.1, bias2=gpu_in[3], residual=gpu_in[4])
+    (out * g.to(cuda)).sum().backward()
+    assert rel_err(out.detach().cpu(), y.detach()) < 2e-6
+    for a, c in zip(gpu_in, ref_in):
+        assert rel_err(a.grad.cpu(), c.grad) < 5e-6

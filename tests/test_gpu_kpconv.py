@@ -92,3 +92,30 @@ def test_kpconv_rejects_cpu_tensors(built_lib):
     m = KPConv(15, 3, 4, 4, 0.06, 0.075)
     with pytest.raises(RuntimeError, match="no CPU path|CUDA"):
         m(torch.zeros(3, 3), torch.zeros(3, 3), torch.zeros(3, 2, dtype=torch.long), torch.zeros(3, 4))
+
+
+@pytest.mark.parametrize("deform", [False, True])
+def test_kpconv_fused_bias_activation_matches_unfused(cuda, kp_impl, deform):
+    """KPConv(..., bias=b, slope=0.1) (epilogue of the contraction) == leaky_relu(KPConv(...) + b), values and grads."""
+    from d3feat.pytorch_b200.blocks import KPConv
+    g = golden("kpconv_deform" if deform else "kpconv_rigid_2k")
+    n, c = (800, 32) if deform else (2000, 64)
+    case = _inputs.kpconv_case(n=n, cin=c, cout=c, seed=104 if deform else 100, deformable=deform, modulated=False)
+    m = KPConv(15, 3, c, c, case["extent"], case["radius"], deformable=deform).to(cuda)
+    m.load_state_dict(case["sd"], strict=True)
+    pts = torch.from_numpy(case["pts"]).to(cuda)
+    inds = torch.from_numpy(g["inds"]).to(cuda)
+    gout = torch.from_numpy(case["g"]).to(cuda)
+    res = []
+    for fused in (False, True):
+        m.zero_grad(set_to_none=True)
+        x = torch.from_numpy(case["x"]).to(cuda).requires_grad_(True)
+        b = torch.linspace(-0.05, 0.05, c, device=cuda).requires_grad_(True)
+        if fused:
+            out = m(pts, pts, inds, x, bias=b, slope=0.1)
+        else:
+            out = torch.nn.functional.leaky_relu(m(pts, pts, inds, x) + b, 0.1)
+        (out * gout).sum().backward()
+        res.append((out.detach(), x.grad, b.grad, m.weights.grad.clone()))
+    for a, r in zip(res[1], res[0]):
+        assert rel_err(a.cpu(), r.cpu()) < 1e-5
