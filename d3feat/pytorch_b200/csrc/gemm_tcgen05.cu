@@ -16,6 +16,7 @@
 // (plain, atomic split-K, or deterministic split-K partials), exactly as the mma.sync kernel.
 #include "common.cuh"
 #include "gemm.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -289,18 +290,290 @@ tc5_gemm_kernel(D3fGemm g) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_d), "r"(TMEM_COLS) : "memory");
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// tc6: the same MMA / TMEM / epilogue path with the A operand fed by a cp.async ring.
+//
+// ncu (round 1d) showed the tc5 kernel latency-bound: one K tile per CTA in flight (held in registers), 12-26 % warps
+// active, ~3 us per K tile when a problem has fewer CTAs than SMs.  Here every thread issues its 16-byte cp.async
+// copies of A for K tile kt+S-1 into a ring of S raw fp32 stages before it converts tile kt, so S-1 A tiles (32-48 KB
+// per CTA, two CTAs per SM) are always in flight and the global-memory latency leaves the per-tile dependency chain:
+//     wait(A tile kt landed) -> barrier -> refill the slot freed by tile kt-1 -> wait(MMAs of kt-1 done)
+//     -> raw stage -> registers -> tf32 hi / remainder -> UMMA-layout stage -> fence + barrier -> 12 tcgen05.mma
+// B (the weight matrix in the NN / NT modes: small and L2-resident) keeps tc5's one-tile register prefetch.
+// Needs a 16-byte aligned A (lda a multiple of 4): everything on the hot path except the K = 15 first layer.
+template <int BN> struct Cfg6 {
+    static constexpr int S = BN == 64 ? 3 : 4;                       // raw A stages
+    static constexpr int RAW_A = BM * BK * 4;                        // bytes
+    static constexpr int OP_BYTES = Cfg<BN>::STAGE_BYTES;            // A_hi | A_lo | B_hi | B_lo in UMMA layout
+    static constexpr int SMEM_BYTES = OP_BYTES + S * RAW_A + 64;     // 32: 110.7 KB, 64: 103.6 KB (2 CTAs/SM); 128: 138.3 KB
+};
+
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
+
+template <bool TA, bool TB, int BN>
+__global__ void __launch_bounds__(NT, BN >= 128 ? 1 : 2)
+tc6_gemm_kernel(D3fGemm g) {
+    constexpr int B_LBO = Cfg<BN>::B_LBO, B_TILE = Cfg<BN>::B_TILE, OP_BYTES = Cfg6<BN>::OP_BYTES;
+    constexpr int S = Cfg6<BN>::S, RAW_A = Cfg6<BN>::RAW_A, RAW_STAGE = Cfg6<BN>::RAW_A;
+    constexpr uint32_t TMEM_COLS = Cfg<BN>::TMEM_COLS;
+    extern __shared__ __align__(128) char smem[];
+    char* raw = smem + OP_BYTES;
+    uint64_t* bars = (uint64_t*)(smem + OP_BYTES + S * RAW_STAGE);
+    uint32_t* tmem_ptr = (uint32_t*)(smem + OP_BYTES + S * RAW_STAGE + 32);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kbeg = blockIdx.z * g.k_per_split, kend = min(g.K, kbeg + g.k_per_split);
+    const int nk = (kend - kbeg + BK - 1) / BK;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(tmem_ptr)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    if (tid == 32) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(&bars[0])), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+
+    const bool b_vec = (g.ldb & 3) == 0 && (((size_t)g.B) & 15) == 0;
+    // 16-byte copies of the A part of K tile `kt` into raw stage kt % S; out-of-range elements are zero-filled
+    auto issue_tile = [&](int kt) {
+        char* ra = raw + (kt % S) * RAW_STAGE;
+        const int k0 = kbeg + kt * BK;
+        if (!TA) {      // A[m][k] -> ra[m][32]
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int ml = (tid >> 3) + 32 * r, k4 = tid & 7;
+                const int m = m0 + ml, k = k0 + k4 * 4;
+                const int nb = (m < g.M) ? 4 * max(0, min(4, kend - k)) : 0;
+                cp_async16(ra + (ml * 8 + k4) * 16, nb ? (const void*)(g.A + (size_t)m * g.lda + k) : (const void*)g.A, nb);
+            }
+        } else {        // A[k][m] -> ra[k][128]
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int kl = (tid >> 5) * 4 + j, m4 = tid & 31;
+                const int k = k0 + kl, m = m0 + m4 * 4;
+                const int nb = (k < kend) ? 4 * max(0, min(4, g.M - m)) : 0;
+                cp_async16(ra + (kl * 32 + m4) * 16, nb ? (const void*)(g.A + (size_t)k * g.lda + m) : (const void*)g.A, nb);
+            }
+        }
+    };
+    float4 rb[BN >= 128 ? BN / 32 : 4];
+    auto load_b = [&](int kt) {     // B part of K tile `kt` -> registers (as tc5)
+        const int k0 = kbeg + kt * BK;
+        if (TB) {       // B[n][k]
+#pragma unroll
+            for (int r = 0; r < BN / 32; ++r) {
+                const int n = n0 + (tid >> 3) + 32 * r, k = k0 + (tid & 7) * 4;
+                rb[r] = (n < g.N) ? ld4g(g.B + (size_t)n * g.ldb + k, kend - k, b_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else if (tid < 2 * BN) {   // B[k][n]: thread = (4 k rows, 4 consecutive n)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = k0 + (tid / (BN / 4)) * 4 + j, n = n0 + (tid % (BN / 4)) * 4;
+                float4 v = (k < kend) ? ld4g(g.B + (size_t)k * g.ldb + n, g.N - n, b_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g.ks && k < kend) { const float sc = g.ks[k]; v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc; }
+                rb[j] = v;
+            }
+        }
+    };
+    // raw A stage / B registers -> tf32 hi + remainder operand tiles (same thread <-> element mapping as tc5)
+    auto convert_tile = [&](int kt) {
+        const char* ra = raw + (kt % S) * RAW_STAGE;
+        char* a_hi = smem;
+        char* a_lo = a_hi + A_TILE;
+        char* b_hi = a_lo + A_TILE;
+        char* b_lo = b_hi + B_TILE;
+        if (!TA) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int m = (tid >> 3) + 32 * r, k4 = tid & 7;
+                st_split(a_hi, a_lo, k4 * A_LBO + (m >> 3) * SBO + (m & 7) * 16, *(const float4*)(ra + (m * 8 + k4) * 16));
+            }
+        } else {
+            const int k4 = tid >> 5, mb = (tid & 31) * 4;
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = *(const float4*)(ra + ((k4 * 4 + j) * 32 + (tid & 31)) * 16);
+            const float t[4][4] = {{v[0].x, v[1].x, v[2].x, v[3].x}, {v[0].y, v[1].y, v[2].y, v[3].y},
+                                   {v[0].z, v[1].z, v[2].z, v[3].z}, {v[0].w, v[1].w, v[2].w, v[3].w}};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int m = mb + e;
+                st_split(a_hi, a_lo, k4 * A_LBO + (m >> 3) * SBO + (m & 7) * 16, make_float4(t[e][0], t[e][1], t[e][2], t[e][3]));
+            }
+        }
+        if (TB) {
+#pragma unroll
+            for (int r = 0; r < BN / 32; ++r) {
+                const int n = (tid >> 3) + 32 * r, k4 = tid & 7;
+                st_split(b_hi, b_lo, k4 * B_LBO + (n >> 3) * SBO + (n & 7) * 16, rb[r]);
+            }
+        } else if (tid < 2 * BN) {
+            const int k4 = tid / (BN / 4), nb = (tid % (BN / 4)) * 4;
+            const float t[4][4] = {{rb[0].x, rb[1].x, rb[2].x, rb[3].x}, {rb[0].y, rb[1].y, rb[2].y, rb[3].y},
+                                   {rb[0].z, rb[1].z, rb[2].z, rb[3].z}, {rb[0].w, rb[1].w, rb[2].w, rb[3].w}};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int n = nb + e;
+                st_split(b_hi, b_lo, k4 * B_LBO + (n >> 3) * SBO + (n & 7) * 16, make_float4(t[e][0], t[e][1], t[e][2], t[e][3]));
+            }
+        }
+    };
+
+    // the ring is primed while warp 0 allocates tensor memory
+#pragma unroll
+    for (int s = 0; s < S - 1; ++s) {
+        if (s < nk) issue_tile(s);
+        cp_async_commit();
+    }
+    if (nk > 0) load_b(0);
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem_d = *tmem_ptr;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<S - 2>();               // this thread's copies of tile kt have landed
+        __syncthreads();                      // ... everyone's have; and everyone is done converting tile kt-1
+        if (kt + S - 1 < nk) issue_tile(kt + S - 1);   // refill the slot tile kt-1 occupied
+        cp_async_commit();
+        if (kt >= 1) mbar_wait(smem_u32(&bars[0]), (kt - 1) & 1, &g_tc5_fail);   // MMAs of tile kt-1 have read the operand stage
+        convert_tile(kt);
+        if (kt + 1 < nk) load_b(kt + 1);      // in flight during the fence / barrier / MMA issue below
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const uint32_t a_hi = smem_u32(smem), a_lo = a_hi + A_TILE;
+            const uint32_t b_hi = a_lo + A_TILE, b_lo = b_hi + B_TILE;
+#pragma unroll
+            for (int ks = 0; ks < BK / 8; ++ks) {
+                const uint32_t ao = ks * 2 * A_LBO, bo = ks * 2 * B_LBO;
+                const uint64_t dah = make_desc(a_hi + ao, A_LBO, SBO), dal = make_desc(a_lo + ao, A_LBO, SBO);
+                const uint64_t dbh = make_desc(b_hi + bo, B_LBO, SBO), dbl = make_desc(b_lo + bo, B_LBO, SBO);
+                mma_tf32(tmem_d, dal, dbh, idesc, (kt | ks) ? 1u : 0u);
+                mma_tf32(tmem_d, dah, dbl, idesc, 1u);
+                mma_tf32(tmem_d, dah, dbh, idesc, 1u);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+                         :: "r"(smem_u32(&bars[0])) : "memory");
+        }
+    }
+    cp_async_wait<0>();
+
+    // ---- epilogue (identical to tc5): TMEM -> registers -> shared C tile -> coalesced global stores
+    if (nk > 0) mbar_wait(smem_u32(&bars[0]), (nk - 1) & 1, &g_tc5_fail);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    constexpr int LDC_S = BN + 4;
+    float* cs = (float*)smem;
+    {
+        const int r_loc = (warp & 3) * 32 + lane, col0 = (warp >> 2) * (BN / 2);
+#pragma unroll
+        for (int part = 0; part < BN / 32; ++part) {
+            uint32_t v[16];
+            const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(col0 + part * 16);
+            if (nk > 0) {
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                             : "r"(taddr) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] = 0u;
+            }
+#pragma unroll
+            for (int e = 0; e < 16; e += 4)
+                *(uint4*)&cs[r_loc * LDC_S + col0 + part * 16 + e] = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+        }
+    }
+    __syncthreads();
+    {
+        const bool atomic = gridDim.z > 1 && !g.partial;
+        constexpr int TPR = BN / 4, RPP = NT / TPR;
+        const int c4 = (tid % TPR) * 4, n = n0 + c4;
+        const bool vec_ok = g.partial ? ((g.N & 3) == 0) : ((g.ldc & 3) == 0 && (((size_t)g.C) & 15) == 0);
+#pragma unroll
+        for (int it = 0; it < BM / RPP; ++it) {
+            const int r_loc = tid / TPR + RPP * it, row = m0 + r_loc;
+            if (row >= g.M || n >= g.N) continue;
+            float4 x = *(const float4*)&cs[r_loc * LDC_S + c4];
+            float xs[4] = {x.x, x.y, x.z, x.w};
+            if (g.partial) {
+                float* dst = g.partial + (size_t)blockIdx.z * g.M * g.N + (size_t)row * g.N + n;
+                if (vec_ok && n + 3 < g.N) *(float4*)dst = x;
+                else for (int e = 0; e < 4; ++e) if (n + e < g.N) dst[e] = xs[e];
+                continue;
+            }
+            const float sc = g.rs ? g.rs[row] : 1.0f;
+            float* dst = g.C + (size_t)row * g.ldc + n;
+            if (atomic) {
+                for (int e = 0; e < 4; ++e) if (n + e < g.N) atomicAdd(dst + e, xs[e] * sc);
+                continue;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float y = xs[e] * sc;
+                if (n + e < g.N) {
+                    if (g.bias) y += g.bias[n + e];
+                    if (g.bias2) y += g.bias2[n + e];
+                    if (g.res) y += g.res[(size_t)row * g.ldr + n + e];
+                }
+                if (g.act) y = y > 0.f ? y : y * g.slope;
+                xs[e] = y;
+            }
+            if (vec_ok && n + 3 < g.N) *(float4*)dst = make_float4(xs[0], xs[1], xs[2], xs[3]);
+            else for (int e = 0; e < 4; ++e) if (n + e < g.N) dst[e] = xs[e];
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_d), "r"(TMEM_COLS) : "memory");
+}
+
 }  // namespace
 
 // launched by d3f_gemm_launch (gemm.cu) with the split decision already made
+// 1 = cp.async-fed kernel (tc6) whenever the operands are 16-byte aligned, 0 = always the register-fed kernel (tc5)
+static int g_tc_pipeline = -1;
+extern "C" void d3f_set_gemm_pipeline(int use_cp_async) { g_tc_pipeline = use_cp_async < 0 ? -1 : (use_cp_async ? 1 : 0); }
+static int tc_pipeline() {
+    if (g_tc_pipeline < 0) {
+        const char* e = getenv("D3F_GEMM_PIPELINE");
+        g_tc_pipeline = (e && e[0] == 'r') ? 0 : 1;     // D3F_GEMM_PIPELINE=reg selects tc5
+    }
+    return g_tc_pipeline;
+}
+
 template <bool TA, bool TB, int BN>
 static int launch_bn(const D3fGemm& g, int splits, cudaStream_t stream) {
+    dim3 grid(d3f_ceil_div(g.N, BN), d3f_ceil_div(g.M, BM), splits);
+    const bool aligned = (g.lda & 3) == 0 && (((size_t)g.A) & 15) == 0;
+    if (tc_pipeline() == 1 && aligned) {
+        static bool attr6_set = false;
+        if (!attr6_set) {
+            D3F_CHECK_CUDA(cudaFuncSetAttribute(tc6_gemm_kernel<TA, TB, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                Cfg6<BN>::SMEM_BYTES));
+            attr6_set = true;
+        }
+        tc6_gemm_kernel<TA, TB, BN><<<grid, NT, Cfg6<BN>::SMEM_BYTES, stream>>>(g);
+        D3F_CHECK_LAUNCH();
+        return D3F_OK;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         D3F_CHECK_CUDA(cudaFuncSetAttribute(tc5_gemm_kernel<TA, TB, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             Cfg<BN>::SMEM_BYTES));
         attr_set = true;
     }
-    dim3 grid(d3f_ceil_div(g.N, BN), d3f_ceil_div(g.M, BM), splits);
     tc5_gemm_kernel<TA, TB, BN><<<grid, NT, Cfg<BN>::SMEM_BYTES, stream>>>(g);
     D3F_CHECK_LAUNCH();
     return D3F_OK;

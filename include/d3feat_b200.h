@@ -234,6 +234,9 @@ int d3f_detection_scores_backward(const float* features, const void* neighbors, 
 /* GEMM back end: 1 = tcgen05.mma + TMEM (default), 0 = legacy mma.sync; d3f_gemm_tcgen05_failed() returns 1 if a
  * tcgen05 kernel ever gave up waiting on its mbarrier (diagnostic, synchronises the device). */
 void d3f_set_gemm_impl(int use_tcgen05);
+/* tcgen05 back end only: 1 = A operand through a cp.async ring (default whenever A is 16-byte aligned), 0 = always the
+ * register-fed kernel, -1 = default (environment D3F_GEMM_PIPELINE=reg selects 0). */
+void d3f_set_gemm_pipeline(int use_cp_async);
 int d3f_gemm_tcgen05_failed(void);
 int d3f_gemm(int trans_a, int trans_b, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
              float* C, int ldc, const float* row_scale, const float* k_scale, const float* bias,

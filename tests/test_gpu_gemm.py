@@ -8,20 +8,25 @@ from _util import rel_err
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["tcgen05", "mma"])
+@pytest.fixture(params=["tcgen05", "tcgen05-reg", "mma"])
 def gemm_impl(request, cuda):
+    """tcgen05 = cp.async-fed kernel where A is 16-byte aligned (register-fed otherwise), tcgen05-reg = always the
+    register-fed kernel, mma = legacy mma.sync kernel."""
     from d3feat.pytorch_b200 import _lib
     lib = _lib.load()
-    lib.d3f_set_gemm_impl(1 if request.param == "tcgen05" else 0)
+    lib.d3f_set_gemm_impl(0 if request.param == "mma" else 1)
+    lib.d3f_set_gemm_pipeline(0 if request.param == "tcgen05-reg" else 1)
     yield request.param
-    if request.param == "tcgen05":
+    if request.param != "mma":
         assert lib.d3f_gemm_tcgen05_failed() == 0, "a tcgen05 GEMM gave up waiting on its mbarrier"
     lib.d3f_set_gemm_impl(1)
+    lib.d3f_set_gemm_pipeline(-1)
 
 
 @pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False)])
 @pytest.mark.parametrize("M,N,K", [(1, 1, 1), (127, 65, 33), (128, 64, 32), (300, 45, 15), (1000, 512, 960),
-                                   (190, 512, 7680), (480, 32, 40000), (4097, 33, 130)])
+                                   (190, 512, 7680), (480, 32, 40000), (4097, 33, 130), (4100, 32, 480), (132, 128, 36),
+                                   (260, 96, 100), (13312, 64, 960)])
 def test_gemm_matches_fp64(cuda, gemm_impl, ta, tb, M, N, K):
     from d3feat.pytorch_b200 import ops
     rng = np.random.default_rng(M * 7 + N * 3 + K)
