@@ -39,6 +39,7 @@ SIGNATURES = {
     "d3f_set_kpconv_impl": (None, [c_i]),
     "d3f_get_kpconv_impl": (c_i, []),
     "d3f_kpconv_set_gather_events": (None, [c_p, c_p]),
+    "d3f_set_scatter_vec": (None, [c_i]),
     "d3f_colsum": (c_i, [c_p, c_i, c_i, c_p, c_p]),
     "d3f_max_pool_forward": (c_i, [c_p, c_p, c_i, c_i64, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "d3f_max_pool_backward": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p]),

@@ -575,13 +575,17 @@ int kp2_correlate_launch(const Kp2Args& a, float* wf, float* wf_unmod, float* in
                : correlate_cg<false, false, 0>(a, HP, grid, warps, smem, wf, wf_unmod, inv_n, min_d2, stream);
 }
 
+// 1 = 128-bit vector reductions where the layer allows it (default), 0 = always scalar reductions (A/B switch)
+static int g_scatter_vec = 1;
+extern "C" void d3f_set_scatter_vec(int use_vec) { g_scatter_vec = use_vec ? 1 : 0; }
+
 int kp2_scatter_launch(const Kp2Args& a, const float* dwf, const float* wf_unmod, float* grad_x, float* grad_kp,
                        float* grad_mod, cudaStream_t stream) {
     const int HP = kp2_hpad(a.H);
     size_t smem;
     const int warps = kp2_warps_per_cta(HP, &smem);
     const int grid = d3f_ceil_div(a.nq, warps);
-    const bool vec = !a.deformed && grad_x && !grad_kp && !grad_mod && (a.cin == 32 || a.cin == 64 || (a.cin & 127) == 0) &&
+    const bool vec = g_scatter_vec && !a.deformed && grad_x && !grad_kp && !grad_mod && (a.cin == 32 || a.cin == 64 || (a.cin & 127) == 0) &&
                      (((size_t)dwf | (size_t)grad_x) & 15) == 0;
     if (vec) return a.idx64 ? scatter_vec<true>(a, HP, grid, warps, smem, dwf, grad_x, stream)
                             : scatter_vec<false>(a, HP, grid, warps, smem, dwf, grad_x, stream);

@@ -238,6 +238,45 @@ __global__ void colsum_kernel(const float* __restrict__ x, int M, int N, int row
     atomicAdd(&out[n], (acc[0] + acc[1]) + (acc[2] + acc[3]));
 }
 
+// Vector version for N = 4 * 2^j (every channel count of the network): the CTA's 256 threads tile [R rows x N/4 float4
+// columns], so a warp reads 512 contiguous bytes per load and every lane is busy even at N = 32 (the scalar kernel
+// above keeps 32 of 128 threads busy there: 25 us for 5 MB in the round-1d profile); 4 independent loads in flight per
+// thread, a shared-memory reduction over the R row groups, one atomicAdd per column per CTA.
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(const float4* __restrict__ x, int M, int nv, int nv_cta, int rows_per_cta, float* __restrict__ out) {
+    __shared__ float4 red[256];
+    const int tid = threadIdx.x;
+    const int cv = tid % nv_cta, rsub = tid / nv_cta, R = 256 / nv_cta;
+    const int col = blockIdx.x * nv_cta + cv;                     // float4 column
+    const int m0 = blockIdx.y * rows_per_cta, m1 = min(M, m0 + rows_per_cta);
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+    int m = m0 + rsub;
+    for (; m + 3 * R < m1; m += 4 * R) {
+        const float4 v0 = x[(size_t)m * nv + col], v1 = x[(size_t)(m + R) * nv + col];
+        const float4 v2 = x[(size_t)(m + 2 * R) * nv + col], v3 = x[(size_t)(m + 3 * R) * nv + col];
+        a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+        a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+        a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
+        a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
+    }
+    for (; m < m1; m += R) {
+        const float4 v0 = x[(size_t)m * nv + col];
+        a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+    }
+    red[tid] = make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y),
+                           (a0.z + a1.z) + (a2.z + a3.z), (a0.w + a1.w) + (a2.w + a3.w));
+    __syncthreads();
+    if (rsub == 0) {
+        float4 t = red[cv];
+        for (int r = 1; r < R; ++r) {
+            const float4 v = red[r * nv_cta + cv];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        float* o = out + 4 * (size_t)col;
+        atomicAdd(o, t.x); atomicAdd(o + 1, t.y); atomicAdd(o + 2, t.z); atomicAdd(o + 3, t.w);
+    }
+}
+
 }  // namespace
 
 extern "C" int d3f_colsum(const float* x, int n_rows, int n_cols, float* out, d3f_stream stream_) {
@@ -246,6 +285,19 @@ extern "C" int d3f_colsum(const float* x, int n_rows, int n_cols, float* out, d3
     D3F_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * n_cols, stream));
     if (n_rows == 0) return D3F_OK;
     D3F_REQUIRE(x, D3F_ERR_INVALID, "null pointer");
+    const int nv = n_cols / 4;
+    if ((n_cols & 3) == 0 && (nv & (nv - 1)) == 0 && (((size_t)x) & 15) == 0) {
+        const int nv_cta = nv < 256 ? nv : 256, R = 256 / nv_cta;
+        const int col_ctas = nv / nv_cta;
+        int row_ctas = d3f_ceil_div(444, col_ctas);              // ~3 CTAs per SM
+        int rpc = d3f_ceil_div(n_rows, row_ctas);
+        if (rpc < 8 * R) rpc = 8 * R;
+        rpc = d3f_ceil_div(rpc, R) * R;
+        row_ctas = d3f_ceil_div(n_rows, rpc);
+        colsum_vec_kernel<<<dim3(col_ctas, row_ctas), 256, 0, stream>>>((const float4*)x, n_rows, nv, nv_cta, rpc, out);
+        D3F_CHECK_LAUNCH();
+        return D3F_OK;
+    }
     const int col_ctas = d3f_ceil_div(n_cols, 128);
     int row_ctas = d3f_ceil_div(592, col_ctas);                  // ~4 CTAs per SM
     int rpc = d3f_ceil_div(n_rows, row_ctas);

@@ -112,3 +112,13 @@ def test_fused_linear_two_biases_residual_autograd(cuda, gemm_impl):
     assert rel_err(out.detach().cpu(), y.detach()) < 2e-6
     for a, c in zip(gpu_in, ref_in):
         assert rel_err(a.grad.cpu(), c.grad) < 5e-6
+
+
+@pytest.mark.parametrize("M,N", [(40000, 32), (13312, 64), (777, 128), (5, 2048), (1, 4), (1000, 40), (333, 7), (4097, 512)])
+def test_colsum(cuda, M, N):
+    from d3feat.pytorch_b200 import ops
+    rng = np.random.default_rng(M + N)
+    x = torch.from_numpy(rng.standard_normal((M, N)).astype(np.float32)).to(cuda)
+    ref = x.double().sum(0)
+    got = ops.colsum(x)
+    assert float((got.double() - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
