@@ -16,42 +16,60 @@ __device__ __forceinline__ long long load_idx(const void* p, size_t off) {
 }
 
 // ------------------------------------------------------------------------------------------- max pool
+// One warp per (query, 128-channel chunk): the deep levels have few queries and many channels (256 x 1024 at level 4),
+// where a warp per query walked 8 chunks x 47 neighbours of dependent index -> row loads (97 us for 1 MB in the
+// round-1d profile).  The neighbour indices of a row are loaded once, 32 at a time, and broadcast by shuffle; four
+// row loads are in flight per lane.  Neighbours are visited in column order with a strict '>' (first maximum wins).
 template <bool IDX64>
 __global__ void mp_forward_kernel(const float* __restrict__ x, const void* __restrict__ inds, long long ld, int nq,
-                                  int ns, int H, int C, float* __restrict__ out, int* __restrict__ arg,
+                                  int ns, int H, int C, int nchunks, float* __restrict__ out, int* __restrict__ arg,
                                   const int* __restrict__ valid_width) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= nq) return;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= nq * nchunks) return;
+    const int qi = w / nchunks, c = (w % nchunks) * 128 + lane * 4;
     // columns >= *valid_width do not exist in the reference's matrix (its width is min(max_count, limit)): they
     // must not contribute the zero shadow row to the max
     if (valid_width) H = min(H, max(*valid_width, 0));
-    for (int c0 = 0; c0 < C; c0 += 128) {
-        const int c = c0 + lane * 4;
-        float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        int who[4] = {-1, -1, -1, -1};
-        for (int h = 0; h < H; ++h) {
-            const long long idx = load_idx<IDX64>(inds, (size_t)warp * ld + h);
-            const bool real = idx >= 0 && idx < ns;
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
-            if (real && c < C) {
-                if (c + 3 < C && (C & 3) == 0) {
-                    const float4 t = *(const float4*)&x[(size_t)idx * C + c];
-                    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-                } else {
-                    for (int e = 0; e < 4; ++e) if (c + e < C) v[e] = x[(size_t)idx * C + c + e];
+    const bool vec = c + 3 < C && (C & 3) == 0;
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int who[4] = {-1, -1, -1, -1};
+    for (int hb = 0; hb < H; hb += 32) {
+        const int cnt = min(32, H - hb);
+        long long mine = -1;
+        if (lane < cnt) mine = load_idx<IDX64>(inds, (size_t)qi * ld + hb + lane);
+        for (int j0 = 0; j0 < cnt; j0 += 4) {
+            long long id[4];
+            float v[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                id[u] = __shfl_sync(0xffffffffu, mine, min(j0 + u, 31));
+                const bool real = j0 + u < cnt && id[u] >= 0 && id[u] < ns;
+                if (!real) id[u] = -1;
+                v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f;
+                if (real && c < C) {
+                    if (vec) {
+                        const float4 t = *(const float4*)&x[(size_t)id[u] * C + c];
+                        v[u][0] = t.x; v[u][1] = t.y; v[u][2] = t.z; v[u][3] = t.w;
+                    } else {
+                        for (int e = 0; e < 4; ++e) if (c + e < C) v[u][e] = x[(size_t)id[u] * C + c + e];
+                    }
                 }
             }
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if (v[e] > best[e]) { best[e] = v[e]; who[e] = real ? (int)idx : -1; }
-        }
+            for (int u = 0; u < 4; ++u)
+                if (j0 + u < cnt) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (c + e < C) {
-                out[(size_t)warp * C + c + e] = H > 0 ? best[e] : 0.f;
-                arg[(size_t)warp * C + c + e] = who[e];
-            }
+                    for (int e = 0; e < 4; ++e)
+                        if (v[u][e] > best[e]) { best[e] = v[u][e]; who[e] = (int)id[u]; }
+                }
+        }
     }
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+        if (c + e < C) {
+            out[(size_t)qi * C + c + e] = H > 0 ? best[e] : 0.f;
+            arg[(size_t)qi * C + c + e] = who[e];
+        }
 }
 
 __global__ void mp_backward_kernel(const float* __restrict__ g, const int* __restrict__ arg, size_t total, int C,
@@ -316,8 +334,11 @@ extern "C" int d3f_max_pool_forward(const float* x, const void* inds, int idx_is
     if (n_queries == 0) return D3F_OK;
     D3F_REQUIRE(x && (inds || n_neighbors == 0) && out && argmax, D3F_ERR_INVALID, "null pointer");
     auto kern = idx_is_64 ? mp_forward_kernel<true> : mp_forward_kernel<false>;
-    kern<<<d3f_ceil_div(n_queries, 8), 256, 0, stream>>>(x, inds, (long long)ld_inds, n_queries, n_supports, n_neighbors,
-                                                        channels, out, argmax, valid_width);
+    const int nchunks = d3f_ceil_div(channels, 128);
+    const long long warps = (long long)n_queries * nchunks;
+    D3F_REQUIRE(warps < (1LL << 28), D3F_ERR_UNSUPPORTED, "max_pool: too many (query, channel chunk) pairs");
+    kern<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(x, inds, (long long)ld_inds, n_queries, n_supports, n_neighbors,
+                                                         channels, nchunks, out, argmax, valid_width);
     D3F_CHECK_LAUNCH();
     return D3F_OK;
 }

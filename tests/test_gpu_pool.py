@@ -17,7 +17,8 @@ def _case(nq, ns, H, C, seed, dtype=torch.int64):
     return x, inds, g
 
 
-@pytest.mark.parametrize("nq,ns,H,C", [(200, 300, 17, 128), (50, 20, 5, 7), (1000, 4000, 36, 64), (3, 3, 1, 1)])
+@pytest.mark.parametrize("nq,ns,H,C", [(200, 300, 17, 128), (50, 20, 5, 7), (1000, 4000, 36, 64), (3, 3, 1, 1),
+                                       (256, 768, 47, 1024), (100, 150, 70, 260), (33, 40, 32, 130)])
 @pytest.mark.parametrize("dtype", [torch.int64, torch.int32])
 def test_max_pool_and_closest_pool(cuda, nq, ns, H, C, dtype):
     from oracle import model_ref
