@@ -36,6 +36,11 @@ SIGNATURES = {
     "d3f_kpconv_backward": (c_i, [c_p, c_p, c_p, c_i, c_i64, c_p, c_p, c_p, c_i, c_p,
                                   c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_i,
                                   c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "d3f_kpconv_backward_ex": (c_i, [c_p, c_p, c_p, c_i, c_i64, c_p, c_p, c_p, c_i, c_p,
+                                     c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_i,
+                                     c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "d3f_neighbors_transpose_workspace_bytes": (c_sz, [c_i]),
+    "d3f_neighbors_transpose": (c_i, [c_p, c_i, c_i64, c_i, c_i, c_i, c_p, c_p, c_p, c_sz, c_p]),
     "d3f_set_kpconv_impl": (None, [c_i]),
     "d3f_get_kpconv_impl": (c_i, []),
     "d3f_kpconv_set_gather_events": (None, [c_p, c_p]),

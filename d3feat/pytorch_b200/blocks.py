@@ -49,13 +49,14 @@ class _KPConvFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, q_pts, s_pts, inds, x, weights, kpoints, modulations, extent, influence, aggregation,
-                deformed, want_min_d2, bias=None, slope=None):
+                deformed, want_min_d2, bias=None, slope=None, t_off=None, t_src=None):
         out, wf, wf_un, inv_n, min_d2 = ops.kpconv_forward(q_pts, s_pts, inds, x, weights, kpoints, extent,
                                                            influence, aggregation, deformed, modulations,
                                                            want_min_d2, bias, slope)
         ctx.save_for_backward(q_pts, s_pts, inds, x, weights, kpoints, modulations, wf, wf_un, inv_n,
                               out if slope is not None else None)
         ctx.cfg = (extent, influence, aggregation, deformed, slope)
+        ctx.transpose = (t_off, t_src) if (t_off is not None and t_src is not None) else None
         if min_d2 is None:
             min_d2 = out.new_empty(0)
         ctx.mark_non_differentiable(min_d2)
@@ -74,8 +75,8 @@ class _KPConvFunction(torch.autograd.Function):
             inds if inds.dtype in (torch.int32, torch.int64) else inds.long(),
             x.float().contiguous(), weights.contiguous(), kpoints.float().contiguous(), extent, influence,
             aggregation, deformed, modulations, wf, wf_un, inv_n, grad_out,
-            need_x=need[3], need_w=need[4], need_kp=need[5] and deformed, need_mod=need[6])
-        return (None, None, None, gx, gw, gkp, gmod, None, None, None, None, None, gbias, None)[:len(need)]
+            need_x=need[3], need_w=need[4], need_kp=need[5] and deformed, need_mod=need[6], transpose=ctx.transpose)
+        return (None, None, None, gx, gw, gkp, gmod, None, None, None, None, None, gbias, None, None, None)[:len(need)]
 
 
 class KPConv(nn.Module):
@@ -142,9 +143,11 @@ class KPConv(nn.Module):
                 modulations = 2 * torch.sigmoid(self.offset_features[:, n_off:])
             self.deformed_KP = unscaled * self.KP_extent + self.kernel_points
             kpoints, deformed = self.deformed_KP, True
+        # transposed neighbour lists attached by engine.collate_static (ops.neighbors_transpose): atomic-free backward
+        t_off, t_src = getattr(neighb_inds, "_d3f_transpose", (None, None))
         out, min_d2 = _KPConvFunction.apply(q_pts, s_pts, neighb_inds, x, self.weights, kpoints, modulations,
                                             float(self.KP_extent), self.KP_influence, self.aggregation_mode,
-                                            deformed, deformed, bias, slope)
+                                            deformed, deformed, bias, slope, t_off, t_src)
         if deformed:
             self.min_d2 = min_d2
         return out

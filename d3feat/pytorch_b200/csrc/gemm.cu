@@ -94,7 +94,8 @@ tc_gemm_kernel(D3fGemm g) {
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const int n = n0 + (tid >> 3) + 32 * r, k = k0 + (tid & 7) * 4;
-                rb[r] = (n < g.N) ? ld4(g.B + (size_t)n * g.ldb + k, kend - k, b_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const size_t kb = g.bblk ? (size_t)(k / g.bblk) * g.bblk_stride + (k % g.bblk) : (size_t)k;
+                rb[r] = (n < g.N) ? ld4(g.B + (size_t)n * g.ldb + kb, kend - k, b_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         } else {    // B[k][n], contiguous along n: 32 k-rows x 16 float4
 #pragma unroll

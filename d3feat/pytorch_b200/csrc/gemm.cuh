@@ -17,6 +17,10 @@ struct D3fGemm {
     const float* bias2;  // optional second bias [N] (UnaryBlock: Linear bias + the learned bias that replaces batch norm)
     const float* res;    // optional residual [M, ldr] added before the activation (ResnetBottleneckBlock shortcut)
     int ldr;
+    // B stored [N, K] (tb) in K blocks: element (n, k) lives at B[(k / bblk) * bblk_stride + n * ldb + k % bblk]
+    // (bblk = 0: plain).  KPConv backward reads W [K_pts, Cin, Cout] as B^T[c][k * Cout + o] this way without a
+    // transposed copy of the weights; bblk must be a multiple of 32.
+    int bblk; long long bblk_stride;
 };
 
 // C[M,N] = act(rs[m] * sum_k opA(m,k) * ks[k] * opB(k,n) + bias[n] + bias2[n] + res[m,n]);  ta: A stored [K,M];  tb: B stored [N,K]

@@ -18,6 +18,10 @@
 #include "gemm.cuh"
 #include <stdlib.h>
 
+#ifndef D3F_GEMM_PIPELINE_DEFAULT
+#define D3F_GEMM_PIPELINE_DEFAULT 0   // tc5 until a variant beats it on the GPU (round 1e: tc6 is slower everywhere)
+#endif
+
 namespace {
 
 constexpr int BM = 128, BK = 32, NT = 256;
@@ -138,7 +142,8 @@ tc5_gemm_kernel(D3fGemm g) {
 #pragma unroll
             for (int r = 0; r < BN / 32; ++r) {
                 const int n = n0 + (tid >> 3) + 32 * r, k = k0 + (tid & 7) * 4;
-                rb[r] = (n < g.N) ? ld4g(g.B + (size_t)n * g.ldb + k, kend - k, b_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const size_t kb = g.bblk ? (size_t)(k / g.bblk) * g.bblk_stride + (k % g.bblk) : (size_t)k;
+                rb[r] = (n < g.N) ? ld4g(g.B + (size_t)n * g.ldb + kb, kend - k, b_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         } else if (tid < 2 * BN) {   // B[k][n]: thread = (4 k rows, 4 consecutive n)
 #pragma unroll
@@ -369,7 +374,8 @@ tc6_gemm_kernel(D3fGemm g) {
 #pragma unroll
             for (int r = 0; r < BN / 32; ++r) {
                 const int n = n0 + (tid >> 3) + 32 * r, k = k0 + (tid & 7) * 4;
-                rb[r] = (n < g.N) ? ld4g(g.B + (size_t)n * g.ldb + k, kend - k, b_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const size_t kb = g.bblk ? (size_t)(k / g.bblk) * g.bblk_stride + (k % g.bblk) : (size_t)k;
+                rb[r] = (n < g.N) ? ld4g(g.B + (size_t)n * g.ldb + kb, kend - k, b_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         } else if (tid < 2 * BN) {   // B[k][n]: thread = (4 k rows, 4 consecutive n)
 #pragma unroll
@@ -539,16 +545,260 @@ tc6_gemm_kernel(D3fGemm g) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_d), "r"(TMEM_COLS) : "memory");
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// tc7: warp-specialised version.  Round 1e measured 2.8 us per K tile per CTA for tc5 (L0 contraction, 2.1 CTAs/SM)
+// and the cp.async ring (tc6) made it worse: the time is not global-load latency but the per-tile SERIALISATION of
+//   MMAs done (mbarrier) -> all 256 threads convert -> __syncthreads -> thread 0 issues 12 MMAs + commit -> ...
+// (ncu source page: 38 % of the stall samples sit at the block barrier, 13 % in the mbarrier wait).  Here
+//   * warps 0-7 (converters) load global -> registers TWO K tiles ahead, split to tf32 hi / remainder and fill one of
+//     two operand stages; each warp signals `full[s]` on its own (fence.proxy.async + __syncwarp + one mbarrier arrive),
+//     so no warp ever waits for another converter;
+//   * warp 8 (one lane) waits for `full[s]` (8 arrivals), issues the 12 tcgen05.mma of the tile and commits them to
+//     `empty[s]`; converters only wait for `empty[s]` when they come back to that stage two tiles later;
+//   * the epilogue (TMEM -> registers -> shared C tile -> global) is tc5's, run by the 8 converter warps.
+constexpr int NT7 = 288, NS7 = 2;
+template <int BN> struct Cfg7 {
+    static constexpr int STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
+    static constexpr int SMEM_BYTES = NS7 * STAGE_BYTES + 128;    // 32: 93.3 KB, 64: 111.7 KB -> 2 CTAs/SM
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" :: "r"(bar) : "memory");
+}
+
+template <bool TA, bool TB, int BN>
+__global__ void __launch_bounds__(NT7, 2)
+tc7_gemm_kernel(D3fGemm g) {
+    constexpr int B_LBO = Cfg<BN>::B_LBO, B_TILE = Cfg<BN>::B_TILE, STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
+    constexpr uint32_t TMEM_COLS = Cfg<BN>::TMEM_COLS;
+    extern __shared__ __align__(128) char smem[];
+    uint64_t* bars = (uint64_t*)(smem + NS7 * STAGE_BYTES);      // full[0], full[1], empty[0], empty[1]
+    uint32_t* tmem_ptr = (uint32_t*)(smem + NS7 * STAGE_BYTES + 64);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kbeg = blockIdx.z * g.k_per_split, kend = min(g.K, kbeg + g.k_per_split);
+    const int nk = (kend - kbeg + BK - 1) / BK;
+    const bool a_vec = (g.lda & 3) == 0 && (((size_t)g.A) & 15) == 0;
+    const bool b_vec = (g.ldb & 3) == 0 && (((size_t)g.B) & 15) == 0;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(tmem_ptr)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    if (tid == 32) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(&bars[0])), "r"(8) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(&bars[1])), "r"(8) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(&bars[2])), "r"(1) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(&bars[3])), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem_d = *tmem_ptr;
+
+    if (warp == 8) {
+        // ---------------- MMA issuer: the whole warp walks the tiles (it must reach the block barriers below
+        // converged), lane 0 issues
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        for (int kt = 0; kt < nk; ++kt) {
+            const int s = kt & 1;
+            mbar_wait(smem_u32(&bars[s]), (kt >> 1) & 1, &g_tc5_fail);          // all 8 converter warps filled stage s
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            if (lane == 0) {
+                const uint32_t a_hi = smem_u32(smem) + s * STAGE_BYTES, a_lo = a_hi + A_TILE;
+                const uint32_t b_hi = a_lo + A_TILE, b_lo = b_hi + B_TILE;
+#pragma unroll
+                for (int ks = 0; ks < BK / 8; ++ks) {
+                    const uint32_t ao = ks * 2 * A_LBO, bo = ks * 2 * B_LBO;
+                    const uint64_t dah = make_desc(a_hi + ao, A_LBO, SBO), dal = make_desc(a_lo + ao, A_LBO, SBO);
+                    const uint64_t dbh = make_desc(b_hi + bo, B_LBO, SBO), dbl = make_desc(b_lo + bo, B_LBO, SBO);
+                    mma_tf32(tmem_d, dal, dbh, idesc, (kt | ks) ? 1u : 0u);
+                    mma_tf32(tmem_d, dah, dbl, idesc, 1u);
+                    mma_tf32(tmem_d, dah, dbh, idesc, 1u);
+                }
+                // arrives on empty[s] once every MMA issued so far has completed (the stage may be refilled)
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+                             :: "r"(smem_u32(&bars[2 + s])) : "memory");
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---------------- converters: global -> registers (two tiles ahead) -> hi / lo operand stage
+        float4 ra[2][4], rb[2][BN >= 128 ? BN / 32 : 4];
+        auto load_tile = [&](int kt, float4 (&a)[4], float4 (&b)[BN >= 128 ? BN / 32 : 4]) {
+            const int k0 = kbeg + kt * BK;
+            if (!TA) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int m = m0 + (tid >> 3) + 32 * r, k = k0 + (tid & 7) * 4;
+                    a[r] = (m < g.M) ? ld4g(g.A + (size_t)m * g.lda + k, kend - k, a_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = k0 + (tid >> 5) * 4 + j, m = m0 + (tid & 31) * 4;
+                    a[j] = (k < kend) ? ld4g(g.A + (size_t)k * g.lda + m, g.M - m, a_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            if (TB) {
+#pragma unroll
+                for (int r = 0; r < BN / 32; ++r) {
+                    const int n = n0 + (tid >> 3) + 32 * r, k = k0 + (tid & 7) * 4;
+                    const size_t kb = g.bblk ? (size_t)(k / g.bblk) * g.bblk_stride + (k % g.bblk) : (size_t)k;
+                    b[r] = (n < g.N) ? ld4g(g.B + (size_t)n * g.ldb + kb, kend - k, b_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else if (tid < 2 * BN) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = k0 + (tid / (BN / 4)) * 4 + j, n = n0 + (tid % (BN / 4)) * 4;
+                    float4 v = (k < kend) ? ld4g(g.B + (size_t)k * g.ldb + n, g.N - n, b_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (g.ks && k < kend) { const float sc = g.ks[k]; v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc; }
+                    b[j] = v;
+                }
+            }
+        };
+        auto store_tile = [&](int s, const float4 (&a)[4], const float4 (&b)[BN >= 128 ? BN / 32 : 4]) {
+            char* a_hi = smem + s * STAGE_BYTES;
+            char* a_lo = a_hi + A_TILE;
+            char* b_hi = a_lo + A_TILE;
+            char* b_lo = b_hi + B_TILE;
+            if (!TA) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int m = (tid >> 3) + 32 * r, k4 = tid & 7;
+                    st_split(a_hi, a_lo, k4 * A_LBO + (m >> 3) * SBO + (m & 7) * 16, a[r]);
+                }
+            } else {
+                const int k4 = tid >> 5, mb = (tid & 31) * 4;
+                const float t[4][4] = {{a[0].x, a[1].x, a[2].x, a[3].x}, {a[0].y, a[1].y, a[2].y, a[3].y},
+                                       {a[0].z, a[1].z, a[2].z, a[3].z}, {a[0].w, a[1].w, a[2].w, a[3].w}};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int m = mb + e;
+                    st_split(a_hi, a_lo, k4 * A_LBO + (m >> 3) * SBO + (m & 7) * 16, make_float4(t[e][0], t[e][1], t[e][2], t[e][3]));
+                }
+            }
+            if (TB) {
+#pragma unroll
+                for (int r = 0; r < BN / 32; ++r) {
+                    const int n = (tid >> 3) + 32 * r, k4 = tid & 7;
+                    st_split(b_hi, b_lo, k4 * B_LBO + (n >> 3) * SBO + (n & 7) * 16, b[r]);
+                }
+            } else if (tid < 2 * BN) {
+                const int k4 = tid / (BN / 4), nb = (tid % (BN / 4)) * 4;
+                const float t[4][4] = {{b[0].x, b[1].x, b[2].x, b[3].x}, {b[0].y, b[1].y, b[2].y, b[3].y},
+                                       {b[0].z, b[1].z, b[2].z, b[3].z}, {b[0].w, b[1].w, b[2].w, b[3].w}};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int n = nb + e;
+                    st_split(b_hi, b_lo, k4 * B_LBO + (n >> 3) * SBO + (n & 7) * 16, make_float4(t[e][0], t[e][1], t[e][2], t[e][3]));
+                }
+            }
+        };
+        // one tile: wait until the MMAs that read stage s two tiles ago are done, fill it, prefetch tile kt + 2, signal
+        auto step = [&](int kt, float4 (&a)[4], float4 (&b)[BN >= 128 ? BN / 32 : 4]) {
+            const int s = kt & 1;
+            if (kt >= NS7) mbar_wait(smem_u32(&bars[2 + s]), ((kt >> 1) - 1) & 1, &g_tc5_fail);
+            store_tile(s, a, b);
+            if (kt + 2 < nk) load_tile(kt + 2, a, b);
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");    // this thread's stores -> async proxy (UMMA)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars[s]));
+        };
+        if (nk > 0) load_tile(0, ra[0], rb[0]);
+        if (nk > 1) load_tile(1, ra[1], rb[1]);
+        for (int kt = 0; kt < nk; kt += 2) {
+            step(kt, ra[0], rb[0]);
+            if (kt + 1 < nk) step(kt + 1, ra[1], rb[1]);
+        }
+        // every MMA has completed once the commit of the last tile has arrived
+        if (nk > 0) mbar_wait(smem_u32(&bars[2 + ((nk - 1) & 1)]), ((nk - 1) >> 1) & 1, &g_tc5_fail);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    }
+
+    // ---- epilogue (tc5's): TMEM -> registers -> shared C tile [128][BN+4] -> coalesced global stores; warp 8 only
+    // takes part in the block barriers
+    constexpr int LDC_S = BN + 4;
+    float* cs = (float*)smem;
+    if (warp < 8) {
+        const int r_loc = (warp & 3) * 32 + lane, col0 = (warp >> 2) * (BN / 2);
+#pragma unroll
+        for (int part = 0; part < BN / 32; ++part) {
+            uint32_t v[16];
+            const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(col0 + part * 16);
+            if (nk > 0) {
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                             : "r"(taddr) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] = 0u;
+            }
+#pragma unroll
+            for (int e = 0; e < 16; e += 4)
+                *(uint4*)&cs[r_loc * LDC_S + col0 + part * 16 + e] = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+        }
+    }
+    __syncthreads();
+    if (warp < 8) {
+        const bool atomic = gridDim.z > 1 && !g.partial;
+        constexpr int TPR = BN / 4, RPP = 256 / TPR;
+        const int c4 = (tid % TPR) * 4, n = n0 + c4;
+        const bool vec_ok = g.partial ? ((g.N & 3) == 0) : ((g.ldc & 3) == 0 && (((size_t)g.C) & 15) == 0);
+#pragma unroll
+        for (int it = 0; it < BM / RPP; ++it) {
+            const int r_loc = tid / TPR + RPP * it, row = m0 + r_loc;
+            if (row >= g.M || n >= g.N) continue;
+            float4 x = *(const float4*)&cs[r_loc * LDC_S + c4];
+            float xs[4] = {x.x, x.y, x.z, x.w};
+            if (g.partial) {
+                float* dst = g.partial + (size_t)blockIdx.z * g.M * g.N + (size_t)row * g.N + n;
+                if (vec_ok && n + 3 < g.N) *(float4*)dst = x;
+                else for (int e = 0; e < 4; ++e) if (n + e < g.N) dst[e] = xs[e];
+                continue;
+            }
+            const float sc = g.rs ? g.rs[row] : 1.0f;
+            float* dst = g.C + (size_t)row * g.ldc + n;
+            if (atomic) {
+                for (int e = 0; e < 4; ++e) if (n + e < g.N) atomicAdd(dst + e, xs[e] * sc);
+                continue;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float y = xs[e] * sc;
+                if (n + e < g.N) {
+                    if (g.bias) y += g.bias[n + e];
+                    if (g.bias2) y += g.bias2[n + e];
+                    if (g.res) y += g.res[(size_t)row * g.ldr + n + e];
+                }
+                if (g.act) y = y > 0.f ? y : y * g.slope;
+                xs[e] = y;
+            }
+            if (vec_ok && n + 3 < g.N) *(float4*)dst = make_float4(xs[0], xs[1], xs[2], xs[3]);
+            else for (int e = 0; e < 4; ++e) if (n + e < g.N) dst[e] = xs[e];
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_d), "r"(TMEM_COLS) : "memory");
+}
+
 }  // namespace
 
 // launched by d3f_gemm_launch (gemm.cu) with the split decision already made
-// 1 = cp.async-fed kernel (tc6) whenever the operands are 16-byte aligned, 0 = always the register-fed kernel (tc5)
+// tcgen05 kernel variant: 0 = tc5 (register-fed, one stage, 3-4 CTAs/SM), 1 = tc6 (A through a cp.async ring; needs a
+// 16-byte aligned A), 2 = tc7 (warp-specialised, two operand stages).  Default from D3F_GEMM_PIPELINE = reg | cpasync | ws.
 static int g_tc_pipeline = -1;
-extern "C" void d3f_set_gemm_pipeline(int use_cp_async) { g_tc_pipeline = use_cp_async < 0 ? -1 : (use_cp_async ? 1 : 0); }
+extern "C" void d3f_set_gemm_pipeline(int variant) { g_tc_pipeline = variant < 0 ? -1 : (variant > 2 ? 2 : variant); }
 static int tc_pipeline() {
     if (g_tc_pipeline < 0) {
         const char* e = getenv("D3F_GEMM_PIPELINE");
-        g_tc_pipeline = (e && e[0] == 'r') ? 0 : 1;     // D3F_GEMM_PIPELINE=reg selects tc5
+        g_tc_pipeline = !e ? D3F_GEMM_PIPELINE_DEFAULT : (e[0] == 'r' ? 0 : (e[0] == 'c' ? 1 : 2));
     }
     return g_tc_pipeline;
 }
@@ -568,6 +818,19 @@ static int launch_bn(const D3fGemm& g, int splits, cudaStream_t stream) {
         D3F_CHECK_LAUNCH();
         return D3F_OK;
     }
+    if constexpr (BN <= 64) {
+        if (tc_pipeline() == 2) {
+            static bool attr7_set = false;
+            if (!attr7_set) {
+                D3F_CHECK_CUDA(cudaFuncSetAttribute(tc7_gemm_kernel<TA, TB, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    Cfg7<BN>::SMEM_BYTES));
+                attr7_set = true;
+            }
+            tc7_gemm_kernel<TA, TB, BN><<<grid, NT7, Cfg7<BN>::SMEM_BYTES, stream>>>(g);
+            D3F_CHECK_LAUNCH();
+            return D3F_OK;
+        }
+    }
     static bool attr_set = false;
     if (!attr_set) {
         D3F_CHECK_CUDA(cudaFuncSetAttribute(tc5_gemm_kernel<TA, TB, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -583,7 +846,8 @@ template <bool TA, bool TB>
 static int launch_mode(const D3fGemm& g, int splits, cudaStream_t stream) {
     if (g.N <= 32) return launch_bn<TA, TB, 32>(g, splits, stream);
     // wide outputs with enough row tiles to fill the chip: 128-wide tiles halve the A re-reads
-    if (g.N >= 256 && d3f_ceil_div(g.M, BM) * d3f_ceil_div(g.N, 128) * splits >= 148) return launch_bn<TA, TB, 128>(g, splits, stream);
+    if (tc_pipeline() != 2 && g.N >= 256 && d3f_ceil_div(g.M, BM) * d3f_ceil_div(g.N, 128) * splits >= 148)
+        return launch_bn<TA, TB, 128>(g, splits, stream);
     return launch_bn<TA, TB, 64>(g, splits, stream);
 }
 

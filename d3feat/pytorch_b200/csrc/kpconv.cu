@@ -454,7 +454,9 @@ size_t kp_layout(KpWs* w, void* base, size_t cap, int nq, int ns, int K, int cin
     w->rowpos = c.take<unsigned char>((size_t)(ns > 0 ? ns : 1));
     const size_t dwf_floats = (size_t)(nq > 0 ? nq : 1) * K * cin;
     w->det_bytes = d3f_gemm_det_workspace_bytes(nq, cout, K * cin);
-    const size_t floats = dwf_floats > w->det_bytes / sizeof(float) ? dwf_floats : w->det_bytes / sizeof(float);
+    size_t floats = dwf_floats > w->det_bytes / sizeof(float) ? dwf_floats : w->det_bytes / sizeof(float);
+    const size_t g_floats = (size_t)(ns > 0 ? ns : 1) * K * cout;   // G of the atomic-free backward (same region)
+    if (g_floats > floats) floats = g_floats;
     w->dwf = c.take<float>(floats);
     w->det = w->dwf;
     return c.off;
@@ -598,6 +600,16 @@ extern "C" int d3f_kpconv_forward_ex(const float* q_pts, const float* s_pts, con
     return d3f_gemm_launch(g, false, false, stream, w.det_bytes ? w.det : &dummy, w.det_bytes);
 }
 
+extern "C" int d3f_kpconv_backward_ex(const float* q_pts, const float* s_pts, const void* inds, int idx_is_64,
+                                      int64_t ld_inds, const float* x, const float* weights,
+                                      const float* kernel_points, int deformed, const float* modulations,
+                                      int nq, int ns, int H, int K, int cin, int cout, float kp_extent,
+                                      int influence, int aggregation, const float* wf, const float* wf_unmod,
+                                      const float* inv_n, const float* grad_out, float* grad_x,
+                                      float* grad_weights, float* grad_kernel_points, float* grad_modulations,
+                                      const int32_t* t_offsets, const int32_t* t_src,
+                                      void* workspace, size_t workspace_bytes, d3f_stream stream_);
+
 extern "C" int d3f_kpconv_backward(const float* q_pts, const float* s_pts, const void* inds, int idx_is_64,
                                    int64_t ld_inds, const float* x, const float* weights,
                                    const float* kernel_points, int deformed, const float* modulations,
@@ -606,6 +618,23 @@ extern "C" int d3f_kpconv_backward(const float* q_pts, const float* s_pts, const
                                    const float* inv_n, const float* grad_out, float* grad_x,
                                    float* grad_weights, float* grad_kernel_points, float* grad_modulations,
                                    void* workspace, size_t workspace_bytes, d3f_stream stream_) {
+    return d3f_kpconv_backward_ex(q_pts, s_pts, inds, idx_is_64, ld_inds, x, weights, kernel_points, deformed, modulations,
+                                  nq, ns, H, K, cin, cout, kp_extent, influence, aggregation, wf, wf_unmod, inv_n, grad_out,
+                                  grad_x, grad_weights, grad_kernel_points, grad_modulations, nullptr, nullptr,
+                                  workspace, workspace_bytes, stream_);
+}
+
+// With the transposed neighbour lists of d3f_neighbors_transpose (t_offsets [Ns+1], t_src), rigid layers whose Cout is
+// a multiple of 32 compute grad_x WITHOUT atomics: G = gather over the lists (kp2t_correlate), grad_x = G x W^T.
+extern "C" int d3f_kpconv_backward_ex(const float* q_pts, const float* s_pts, const void* inds, int idx_is_64,
+                                      int64_t ld_inds, const float* x, const float* weights,
+                                      const float* kernel_points, int deformed, const float* modulations,
+                                      int nq, int ns, int H, int K, int cin, int cout, float kp_extent,
+                                      int influence, int aggregation, const float* wf, const float* wf_unmod,
+                                      const float* inv_n, const float* grad_out, float* grad_x,
+                                      float* grad_weights, float* grad_kernel_points, float* grad_modulations,
+                                      const int32_t* t_offsets, const int32_t* t_src,
+                                      void* workspace, size_t workspace_bytes, d3f_stream stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc = kp_check(nq, ns, H, K, cin, cout);
     if (rc) return rc;
@@ -629,6 +658,17 @@ extern "C" int d3f_kpconv_backward(const float* q_pts, const float* s_pts, const
     }
     const bool need_scatter = grad_x || (deformed && (grad_kernel_points || grad_modulations));
     if (!need_scatter) return D3F_OK;
+    if (grad_x && t_offsets && t_src && !deformed && !modulations && kp_impl() >= 1 && kp2t_supported(nq, cout) && ns > 0) {
+        // atomic-free: G[j,k,o] over the transposed lists, then grad_x[j,c] = sum_{k,o} G[j,k,o] W[k,c,o]
+        float* G = w.dwf;
+        Kp2tArgs ta{q_pts, s_pts, t_offsets, t_src, grad_out, inv_n, kernel_points, nq, ns, K, cout, kp_extent, influence,
+                    aggregation};
+        rc = kp2t_correlate_launch(ta, G, stream);
+        if (rc) return rc;
+        D3fGemm g{ns, cin, K * cout, G, K * cout, weights, cout, grad_x, cin, nullptr, nullptr, nullptr, 0, 0.f, 0, nullptr,
+                  nullptr, nullptr, 0, cout, (long long)cin * cout};
+        return d3f_gemm_launch(g, false, true, stream);
+    }
     // dwf[i, kc] = inv_n[i] * sum_o g[i, o] * W[kc, o]
     {
         D3fGemm g{nq, KC, cout, grad_out, cout, weights, cout, w.dwf, KC, inv_n, nullptr, nullptr, 0, 0.f, 0, nullptr};

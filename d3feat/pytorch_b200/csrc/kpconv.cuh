@@ -16,3 +16,12 @@ int kp2_scatter_launch(const Kp2Args& a, const float* dwf, const float* wf_unmod
                        float* grad_mod, cudaStream_t stream);
 // the v2 kernels need one warp's shared-memory slab to fit and 32-bit row offsets (Ns * Cin < 2^31)
 bool kp2_supported(int H, int ns, int cin);
+
+// atomic-free backward (rigid layers): forward-style gather over the transposed neighbour lists of transpose.cu
+struct Kp2tArgs {
+    const float* q; const float* s; const int* t_off; const int* t_src; const float* g; const float* inv_n;
+    const float* kp; int nq, ns, K, cout; float extent; int influence, aggregation;
+};
+bool kp2t_supported(int nq, int cout);
+// G [ns, K, cout] = sum over listing queries of w * inv_n * grad_out rows
+int kp2t_correlate_launch(const Kp2tArgs& a, float* G, cudaStream_t stream);

@@ -484,6 +484,138 @@ kp2_scatter_vec_kernel(Kp2Args a, int HP, const float* __restrict__ dwf, float* 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ backward, atomic-free
+// G[j, k, o] = sum over the queries i that list support j of  w[i, k, h(i,j)] * inv_n[i] * g[i, o]
+// -- the forward gather over the TRANSPOSED neighbour lists (t_off / t_src, transpose.cu), reading rows of the output
+// gradient instead of rows of x.  dx = G [Ns, K*Cout] x W^T then is one GEMM (kpconv.cu).  One warp per support point,
+// lists walked in chunks of HT entries with the accumulators kept in registers; rigid layers, Cout % 32 == 0.
+constexpr int HT = 64;
+__host__ __device__ inline size_t kp2t_warp_floats() { return (size_t)HT * (WS + 5); }   // w_s | rec_s (float4) | idx_s
+
+template <int CG>
+__global__ void __launch_bounds__(256)
+kp2t_correlate_kernel(Kp2tArgs a, float* __restrict__ G) {
+    extern __shared__ float4 smem_f4[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (j >= a.ns) return;
+    float* w_s = (float*)smem_f4 + (size_t)warp * kp2t_warp_floats();
+    float4* rec_s = (float4*)(w_s + HT * WS);
+    int* idx_s = (int*)(rec_s + HT);
+    const float sx = a.s[3 * (size_t)j], sy = a.s[3 * (size_t)j + 1], sz = a.s[3 * (size_t)j + 2];
+    const int e0 = a.t_off[j], e1 = a.t_off[j + 1];
+    const int k = lane & 15, hh = lane >> 4;
+    const bool kvalid = k < a.K;
+    float kx = 0.f, ky = 0.f, kz = 0.f;
+    if (kvalid) { kx = a.kp[3 * k]; ky = a.kp[3 * k + 1]; kz = a.kp[3 * k + 2]; }
+    const float inv_ext = 1.0f / a.extent;
+    const float sigma = a.extent * 0.3f, gden = 2.0f * sigma * sigma + 1e-9f;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int cout = a.cout;
+    const float* __restrict__ g = a.g;
+
+    for (int c0 = 0; c0 < cout; c0 += 32 * CG) {
+        float acc[CG][4][4];
+#pragma unroll
+        for (int jj = 0; jj < CG; ++jj)
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[jj][e][i] = 0.f;
+        for (int base = e0; base < e1; base += HT) {
+            const int cnt = min(HT, e1 - base), cnt8 = (cnt + 7) & ~7;
+            // ---- A: lanes over list entries: (s_j - q_i, inv_n[i]) records
+            for (int h0 = 0; h0 < cnt8; h0 += 32) {
+                const int h = h0 + lane;
+                if (h < cnt8) {
+                    int i = -1;
+                    float rx = SHADOW, ry = SHADOW, rz = SHADOW, sc = 0.f;
+                    if (h < cnt) {
+                        i = a.t_src[base + h];
+                        rx = sx - a.q[3 * (size_t)i]; ry = sy - a.q[3 * (size_t)i + 1]; rz = sz - a.q[3 * (size_t)i + 2];
+                        sc = a.inv_n[i];
+                    }
+                    rec_s[h] = make_float4(rx, ry, rz, sc);
+                    idx_s[h] = i;
+                }
+            }
+            __syncwarp();
+            // ---- B: lanes over (entry parity, kernel point); the density normalisation rides in the weight
+            for (int t = 0; t < (cnt8 >> 1); ++t) {
+                const int h = 2 * t + hh;
+                const float4 r = rec_s[h];
+                const float dx = r.x - kx, dy = r.y - ky, dz = r.z - kz;
+                const float sq = dx * dx + dy * dy + dz * dz;
+                float w;
+                if (a.influence == D3F_INFLUENCE_LINEAR) w = fmaxf(1.0f - fast_sqrt(sq) * inv_ext, 0.0f);
+                else if (a.influence == D3F_INFLUENCE_GAUSSIAN) w = expf(-sq / gden);
+                else w = 1.0f;
+                if (a.aggregation == D3F_AGGREGATION_CLOSEST) {
+                    float bs = kvalid ? sq : INFINITY;
+                    int bk = k;
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) {
+                        const float os = __shfl_xor_sync(FULL, bs, o);
+                        const int ok = __shfl_xor_sync(FULL, bk, o);
+                        if (os < bs || (os == bs && ok < bk)) { bs = os; bk = ok; }
+                    }
+                    if (bk != k) w = 0.f;
+                }
+                w_s[h * WS + k] = kvalid ? w * r.w : 0.f;      // r.w = 0 for the padding entries
+            }
+            __syncwarp();
+            // ---- C: G[16 x 32*CG] += w[16 x 8] * g_rows[8 x 32*CG] per 8 entries, 3xTF32
+            for (int h0 = 0; h0 < cnt8; h0 += 8) {
+                const unsigned ra = (unsigned)max(idx_s[h0 + tq], 0) * (unsigned)cout;
+                const unsigned rb = (unsigned)max(idx_s[h0 + tq + 4], 0) * (unsigned)cout;
+                float4 xa[CG], xb[CG];
+#pragma unroll
+                for (int jj = 0; jj < CG; ++jj) {
+                    const float* gc = g + min(c0 + jj * 32 + 4 * gq, cout - 4);
+                    xa[jj] = __ldg((const float4*)(gc + ra));
+                    xb[jj] = __ldg((const float4*)(gc + rb));
+                }
+                const float* wq = w_s + (h0 + tq) * WS + gq;
+                uint32_t ah[4], al[4];
+                split_tf32(wq[0], ah[0], al[0]);
+                split_tf32(wq[8], ah[1], al[1]);
+                split_tf32(wq[4 * WS], ah[2], al[2]);
+                split_tf32(wq[4 * WS + 8], ah[3], al[3]);
+#pragma unroll
+                for (int jj = 0; jj < CG; ++jj) {
+                    const float va[4] = {xa[jj].x, xa[jj].y, xa[jj].z, xa[jj].w};
+                    const float vb[4] = {xb[jj].x, xb[jj].y, xb[jj].z, xb[jj].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        uint32_t bh[2], bl[2];
+                        split_tf32(va[e], bh[0], bl[0]);
+                        split_tf32(vb[e], bh[1], bl[1]);
+                        mma_tf32(acc[jj][e], al, bh);
+                        mma_tf32(acc[jj][e], ah, bl);
+                        mma_tf32(acc[jj][e], ah, bh);
+                    }
+                }
+            }
+            __syncwarp();      // the next chunk overwrites the slab
+        }
+#pragma unroll
+        for (int jj = 0; jj < CG; ++jj)
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int kk = gq + 8 * half;
+                if (kk >= a.K) continue;
+#pragma unroll
+                for (int nn = 0; nn < 2; ++nn) {
+                    const int c = c0 + jj * 32 + 4 * (2 * tq + nn);
+                    if (c >= cout) continue;
+                    const int i = 2 * half + nn;
+                    *(float4*)(G + ((size_t)j * a.K + kk) * cout + c) =
+                        make_float4(acc[jj][0][i], acc[jj][1][i], acc[jj][2][i], acc[jj][3][i]);
+                }
+            }
+    }
+}
+
 int kp2_warps_per_cta(int HP, size_t* smem) {
     const size_t per = kp2_warp_floats(HP) * sizeof(float);
     int warps = 8;
@@ -595,4 +727,24 @@ int kp2_scatter_launch(const Kp2Args& a, const float* dwf, const float* wf_unmod
     }
     if (a.deformed) return scatter_cg<false, true>(a, HP, grid, warps, smem, dwf, wf_unmod, grad_x, grad_kp, grad_mod, stream);
     return scatter_cg<false, false>(a, HP, grid, warps, smem, dwf, wf_unmod, grad_x, grad_kp, grad_mod, stream);
+}
+
+bool kp2t_supported(int nq, int cout) { return (cout & 31) == 0 && (long long)nq * cout < (1LL << 31); }
+
+int kp2t_correlate_launch(const Kp2tArgs& a, float* G, cudaStream_t stream) {
+    if (a.ns <= 0) return D3F_OK;
+    const int warps = 8;
+    const size_t smem = kp2t_warp_floats() * sizeof(float) * warps;
+    const int grid = d3f_ceil_div(a.ns, warps);
+#define KP2T_GO(CG_)                                                                                      \
+    do {                                                                                                  \
+        auto kern = kp2t_correlate_kernel<CG_>;                                                           \
+        int rc_ = kp2_set_smem(kern, smem);                                                               \
+        if (rc_) return rc_;                                                                              \
+        kern<<<grid, warps * 32, smem, stream>>>(a, G);                                                   \
+    } while (0)
+    if (a.cout <= 32) KP2T_GO(1); else if (a.cout <= 64) KP2T_GO(2); else KP2T_GO(4);
+#undef KP2T_GO
+    D3F_CHECK_LAUNCH();
+    return D3F_OK;
 }

@@ -1,0 +1,99 @@
+// Transposed neighbour lists (CSR) for the atomic-free KPConv backward.
+//
+// KPConv's gradient with respect to the support features is
+//     dx[j, c] = sum over (i, h) with idx[i, h] = j of  sum_k w[i, k, h] * dwf[i, k, c]
+// i.e. a sum over the queries i that list support j.  Walking the neighbour matrix row by row (query by query) turns
+// it into 45 M float reductions at level 0, and the LSU retires about one reduction lane per 1.3 cycles per SM: 200 us,
+// whatever the kernel around it does (round 1e micro-benchmark).  Walking it COLUMN-wise needs, for every support j,
+// the list of queries that reference it: this file builds that list once per neighbour matrix (count -> scan -> fill),
+// and kp2t_correlate (kpconv2.cu) then computes the backward as a forward gather over it -- no atomics.
+#include "common.cuh"
+
+namespace {
+
+template <bool IDX64>
+__global__ void nt_count_kernel(const void* __restrict__ inds, long long ld, int nq, int H, int ns, int* __restrict__ cnt) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)nq * H) return;
+    const int i = (int)(t / H), h = (int)(t % H);
+    const long long j = IDX64 ? ((const long long*)inds)[(size_t)i * ld + h] : (long long)((const int*)inds)[(size_t)i * ld + h];
+    if (j >= 0 && j < ns) atomicAdd(&cnt[j], 1);
+}
+
+// in place: cnt[0..n) -> exclusive offsets, cnt[n] = total; cursor[0..n) = offsets.  One CTA of 1024 threads.
+__global__ void __launch_bounds__(1024) nt_scan_kernel(int* __restrict__ cnt, int* __restrict__ cursor, int n) {
+    __shared__ int warp_sum[32];
+    __shared__ int carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int chunk = (n + 1023) / 1024;
+    const int i0 = min(n, tid * chunk), i1 = min(n, i0 + chunk);
+    int local = 0;
+    for (int i = i0; i < i1; ++i) local += cnt[i];
+    int incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int ws = warp_sum[lane], wi = ws;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += v;
+        }
+        warp_sum[lane] = wi - ws;          // exclusive prefix of the warp totals
+        if (lane == 31) carry_s = wi;      // grand total
+    }
+    __syncthreads();
+    int run = warp_sum[warp] + incl - local;
+    for (int i = i0; i < i1; ++i) {
+        const int c = cnt[i];
+        cnt[i] = run; cursor[i] = run;
+        run += c;
+    }
+    if (tid == 0) cnt[n] = carry_s;
+}
+
+template <bool IDX64>
+__global__ void nt_fill_kernel(const void* __restrict__ inds, long long ld, int nq, int H, int ns, int* __restrict__ cursor,
+                               int* __restrict__ src) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)nq * H) return;
+    const int i = (int)(t / H), h = (int)(t % H);
+    const long long j = IDX64 ? ((const long long*)inds)[(size_t)i * ld + h] : (long long)((const int*)inds)[(size_t)i * ld + h];
+    if (j >= 0 && j < ns) src[atomicAdd(&cursor[j], 1)] = i;
+}
+
+}  // namespace
+
+extern "C" size_t d3f_neighbors_transpose_workspace_bytes(int n_supports) {
+    return d3f_align(sizeof(int) * (size_t)(n_supports > 0 ? n_supports : 1));
+}
+
+extern "C" int d3f_neighbors_transpose(const void* inds, int idx_is_64, int64_t ld_inds, int nq, int ns, int H,
+                                       int32_t* t_offsets, int32_t* t_src, void* workspace, size_t workspace_bytes,
+                                       d3f_stream stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    D3F_REQUIRE(nq >= 0 && ns >= 0 && H >= 0 && t_offsets, D3F_ERR_INVALID, "bad arguments");
+    D3F_REQUIRE(workspace && workspace_bytes >= d3f_neighbors_transpose_workspace_bytes(ns), D3F_ERR_WORKSPACE,
+                "workspace too small");
+    D3F_CHECK_CUDA(cudaMemsetAsync(t_offsets, 0, sizeof(int32_t) * ((size_t)ns + 1), stream));
+    const long long total = (long long)nq * H;
+    if (total == 0 || ns == 0) return D3F_OK;
+    D3F_REQUIRE(inds && t_src, D3F_ERR_INVALID, "null pointer");
+    D3F_REQUIRE(total < (1LL << 31), D3F_ERR_UNSUPPORTED, "neighbour matrix too large for 32-bit offsets");
+    int* cursor = (int*)workspace;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (idx_is_64) nt_count_kernel<true><<<blocks, 256, 0, stream>>>(inds, (long long)ld_inds, nq, H, ns, t_offsets);
+    else nt_count_kernel<false><<<blocks, 256, 0, stream>>>(inds, (long long)ld_inds, nq, H, ns, t_offsets);
+    D3F_CHECK_LAUNCH();
+    nt_scan_kernel<<<1, 1024, 0, stream>>>(t_offsets, cursor, ns);
+    D3F_CHECK_LAUNCH();
+    if (idx_is_64) nt_fill_kernel<true><<<blocks, 256, 0, stream>>>(inds, (long long)ld_inds, nq, H, ns, cursor, t_src);
+    else nt_fill_kernel<false><<<blocks, 256, 0, stream>>>(inds, (long long)ld_inds, nq, H, ns, cursor, t_src);
+    D3F_CHECK_LAUNCH();
+    return D3F_OK;
+}

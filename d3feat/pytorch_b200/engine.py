@@ -54,7 +54,8 @@ def _pyramid_levels(config):
     return levels
 
 
-def collate_static(pts0, pts1, feat0, feat1, corr, dist_keypts, config, limits, caps, lengths=None, side_stream=None):
+def collate_static(pts0, pts1, feat0, feat1, corr, dist_keypts, config, limits, caps, lengths=None, side_stream=None,
+                   transposes=False):
     """Same pyramid as dataloader.collate_fn_descriptor (reference dataloader.py:69-189) on
     capacity-padded tensors, with no host synchronisation.  Returns (batch dict, status int32 tensor);
     status must be all zeros for the batch to be valid (checked by the caller after the step).
@@ -100,8 +101,10 @@ def collate_static(pts0, pts1, feat0, feat1, corr, dist_keypts, config, limits, 
                 ready.append(None)
             r_normal *= 2
 
-    def search(q, s, ql, sl, r, limit, pad):
+    def search(q, s, ql, sl, r, limit, pad, transpose=False):
         idx, info = ops.radius_neighbors_raw(q, s, ql, sl, r, int(limit), torch.int32, None, False, pad_index=pad)
+        if transpose:   # training: "which queries list support j", consumed by every KPConv backward over this matrix
+            idx._d3f_transpose = ops.neighbors_transpose(idx, s.shape[0])
         flags.append(info[1:2])           # 1 = a row overflowed the candidate buffer
         # the reference's matrix has min(max_count, limit) columns (dataloader.py:64-65): a row that fills it holds
         # no shadow index, which max_pool / the eval-mode detection gate can see -> keep that width on the device
@@ -114,14 +117,14 @@ def collate_static(pts0, pts1, feat0, feat1, corr, dist_keypts, config, limits, 
         cap = caps[l]
         if has_conv:
             r = r_normal * config.deform_radius / config.conv_radius if deform_conv else r_normal
-            conv_i = search(pts[l], pts[l], lens[l], lens[l], r, limits[l], cap)
+            conv_i = search(pts[l], pts[l], lens[l], lens[l], r, limits[l], cap, transposes and not deform_conv)
         else:
             conv_i = empty_idx
         if has_pool:
             if ready[l + 1] is not None:
                 main.wait_event(ready[l + 1])
             r = r_normal * config.deform_radius / config.conv_radius if deform_pool else r_normal
-            pool_i = search(pts[l + 1], pts[l], lens[l + 1], lens[l], r, limits[l], cap)
+            pool_i = search(pts[l + 1], pts[l], lens[l + 1], lens[l], r, limits[l], cap, transposes and not deform_pool)
             up_i = search(pts[l], pts[l + 1], lens[l], lens[l + 1], 2 * r, limits[l], caps[l + 1])
         else:
             pool_i, up_i = empty_idx, empty_idx
@@ -172,7 +175,8 @@ class PairStep:
     # -- the step on the static input buffers
     def _body(self):
         cfg = self.config
-        batch, status = collate_static(*self.inputs, cfg, self.limits, self.caps, self.lengths0, self.side_stream)
+        batch, status = collate_static(*self.inputs, cfg, self.limits, self.caps, self.lengths0, self.side_stream,
+                                       transposes=self.optimizer is not None)
         feats, scores = self.model(batch)
         c = batch['corr']
         ia, ip = c[:, 0], c[:, 1] + self.n0

@@ -201,8 +201,33 @@ def kpconv_forward(q_pts, s_pts, inds, x, weights, kernel_points, extent, influe
     return out, wf, wf_un, inv_n, min_d2
 
 
+def neighbors_transpose(inds, n_supports):
+    """CSR lists "which queries reference support j" of a neighbour matrix [Nq, H] (d3f_neighbors_transpose):
+    (t_offsets int32 [n_supports + 1], t_src int32 [Nq * H]).  Feeds the atomic-free KPConv backward."""
+    lib = _lib.load()
+    if not inds.is_cuda:
+        raise RuntimeError("d3feat.pytorch_b200: `inds` must be a CUDA tensor")
+    if inds.dtype not in (torch.int32, torch.int64):
+        inds = inds.long()
+    if inds.dim() != 2 or (inds.shape[1] > 0 and inds.stride(-1) != 1):
+        inds = inds.contiguous()
+    nq, H = inds.shape
+    dev = inds.device
+    t_off = torch.empty(int(n_supports) + 1, dtype=torch.int32, device=dev)
+    t_src = torch.empty(max(nq * H, 1), dtype=torch.int32, device=dev)
+    ws = _ws(lib.d3f_neighbors_transpose_workspace_bytes(int(n_supports)), dev)
+    global launch_count
+    launch_count += 1
+    with _Timed(("neighbors_transpose", nq, int(n_supports), H)):
+        _lib.check(lib.d3f_neighbors_transpose(_p(inds), 1 if inds.dtype == torch.int64 else 0, inds.stride(0) if H > 0 else 0,
+                                               nq, int(n_supports), H, _p(t_off), _p(t_src), _p(ws), ws.numel(), _stream()))
+    return t_off, t_src
+
+
 def kpconv_backward(q_pts, s_pts, inds, x, weights, kernel_points, extent, influence, aggregation, deformed,
-                    modulations, wf, wf_un, inv_n, grad_out, need_x, need_w, need_kp, need_mod):
+                    modulations, wf, wf_un, inv_n, grad_out, need_x, need_w, need_kp, need_mod, transpose=None):
+    """d3f_kpconv_backward_ex.  `transpose` = (t_offsets, t_src) from neighbors_transpose selects the atomic-free
+    grad_x where the layer allows it (rigid, Cout % 32 == 0)."""
     lib = _lib.load()
     dev = x.device
     nq, ns, H = q_pts.shape[0], s_pts.shape[0], inds.shape[1]
@@ -216,12 +241,13 @@ def kpconv_backward(q_pts, s_pts, inds, x, weights, kernel_points, extent, influ
     global launch_count
     launch_count += 1
     with _Timed(("kpconv_bwd", nq, ns, H, cin, cout, bool(deformed))):
-      _lib.check(lib.d3f_kpconv_backward(_p(q_pts), _p(s_pts), _p(inds), 1 if inds.dtype == torch.int64 else 0,
-                                       inds.stride(0) if H > 0 else 0, _p(x), _p(weights), _p(kernel_points),
-                                       1 if deformed else 0, _p(modulations), nq, ns, H, K, cin, cout,
-                                       float(extent), INFLUENCE[influence], AGGREGATION[aggregation],
-                                       _p(wf), _p(wf_un), _p(inv_n), _p(grad_out), _p(gx), _p(gw), _p(gkp), _p(gmod),
-                                       _p(ws), ws.numel(), _stream()))
+      t_off, t_src = transpose if transpose is not None else (None, None)
+      _lib.check(lib.d3f_kpconv_backward_ex(_p(q_pts), _p(s_pts), _p(inds), 1 if inds.dtype == torch.int64 else 0,
+                                          inds.stride(0) if H > 0 else 0, _p(x), _p(weights), _p(kernel_points),
+                                          1 if deformed else 0, _p(modulations), nq, ns, H, K, cin, cout,
+                                          float(extent), INFLUENCE[influence], AGGREGATION[aggregation],
+                                          _p(wf), _p(wf_un), _p(inv_n), _p(grad_out), _p(gx), _p(gw), _p(gkp), _p(gmod),
+                                          _p(t_off), _p(t_src), _p(ws), ws.numel(), _stream()))
     return gx, gw, gkp, gmod
 
 

@@ -158,6 +158,29 @@ int d3f_kpconv_backward(const float* q_pts, const float* s_pts, const void* inds
                         float* grad_modulations,
                         void* workspace, size_t workspace_bytes, d3f_stream stream);
 
+/* Transposed neighbour lists for the atomic-free backward: for every support j the queries i with inds[i, h] = j
+ * (any h), as CSR:  t_offsets [n_supports + 1] i32,  t_src [n_queries * n_neighbors capacity] i32 (query indices; the
+ * order inside a list is unspecified).  One call per neighbour matrix; every KPConv layer that uses the matrix shares it.
+ * d3f_kpconv_backward_ex = d3f_kpconv_backward plus (t_offsets, t_src): when both are given and the layer is rigid with
+ * Cout % 32 == 0, grad_x is computed as a forward-style gather over the lists followed by one GEMM with W^T -- no float
+ * atomics (the 45 M reductions of level 0 cost 200 us however they are issued) and a deterministic result per list order;
+ * otherwise it falls back to the scatter of d3f_kpconv_backward.  The KPConv workspace covers both. */
+size_t d3f_neighbors_transpose_workspace_bytes(int n_supports);
+int d3f_neighbors_transpose(const void* inds, int idx_is_64, int64_t ld_inds, int n_queries, int n_supports,
+                            int n_neighbors, int32_t* t_offsets, int32_t* t_src, void* workspace, size_t workspace_bytes,
+                            d3f_stream stream);
+int d3f_kpconv_backward_ex(const float* q_pts, const float* s_pts, const void* inds, int idx_is_64,
+                           int64_t ld_inds, const float* x, const float* weights,
+                           const float* kernel_points, int deformed, const float* modulations,
+                           int n_queries, int n_supports, int n_neighbors, int K, int c_in, int c_out,
+                           float kp_extent, int influence, int aggregation,
+                           const float* wf, const float* wf_unmod, const float* inv_n,
+                           const float* grad_out,
+                           float* grad_x, float* grad_weights, float* grad_kernel_points,
+                           float* grad_modulations,
+                           const int32_t* t_offsets, const int32_t* t_src,
+                           void* workspace, size_t workspace_bytes, d3f_stream stream);
+
 /* ------------------------------------------------------------------------------------------
  * Pairwise descriptor distance + descriptor loss + detector loss.  Replaces cdist,
  * CircleLoss.forward / ContrastiveLoss.forward and DetLoss.forward (utils/loss.py:8-44, 111-141,
@@ -236,9 +259,10 @@ int d3f_detection_scores_backward(const float* features, const void* neighbors, 
 /* GEMM back end: 1 = tcgen05.mma + TMEM (default), 0 = legacy mma.sync; d3f_gemm_tcgen05_failed() returns 1 if a
  * tcgen05 kernel ever gave up waiting on its mbarrier (diagnostic, synchronises the device). */
 void d3f_set_gemm_impl(int use_tcgen05);
-/* tcgen05 back end only: 1 = A operand through a cp.async ring (default whenever A is 16-byte aligned), 0 = always the
- * register-fed kernel, -1 = default (environment D3F_GEMM_PIPELINE=reg selects 0). */
-void d3f_set_gemm_pipeline(int use_cp_async);
+/* tcgen05 back end only, kernel variant: 0 = register-fed, one operand stage, 3-4 CTAs/SM; 1 = A operand through a
+ * cp.async ring (needs a 16-byte aligned A); 2 = warp-specialised (8 converter warps + 1 MMA warp, two operand stages);
+ * -1 = default (environment D3F_GEMM_PIPELINE = reg | cpasync | ws, else the library's built-in choice). */
+void d3f_set_gemm_pipeline(int variant);
 int d3f_gemm_tcgen05_failed(void);
 int d3f_gemm(int trans_a, int trans_b, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
              float* C, int ldc, const float* row_scale, const float* k_scale, const float* bias,

@@ -8,14 +8,14 @@ from _util import rel_err
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["tcgen05", "tcgen05-reg", "mma"])
+@pytest.fixture(params=["tcgen05-reg", "tcgen05-cpasync", "tcgen05-ws", "mma"])
 def gemm_impl(request, cuda):
-    """tcgen05 = cp.async-fed kernel where A is 16-byte aligned (register-fed otherwise), tcgen05-reg = always the
-    register-fed kernel, mma = legacy mma.sync kernel."""
+    """tcgen05-reg = register-fed one-stage kernel, tcgen05-cpasync = A through a cp.async ring (where A is 16-byte
+    aligned), tcgen05-ws = warp-specialised two-stage kernel, mma = legacy mma.sync kernel."""
     from d3feat.pytorch_b200 import _lib
     lib = _lib.load()
     lib.d3f_set_gemm_impl(0 if request.param == "mma" else 1)
-    lib.d3f_set_gemm_pipeline(0 if request.param == "tcgen05-reg" else 1)
+    lib.d3f_set_gemm_pipeline({"tcgen05-reg": 0, "tcgen05-cpasync": 1, "tcgen05-ws": 2}.get(request.param, -1))
     yield request.param
     if request.param != "mma":
         assert lib.d3f_gemm_tcgen05_failed() == 0, "a tcgen05 GEMM gave up waiting on its mbarrier"

@@ -119,3 +119,45 @@ def test_kpconv_fused_bias_activation_matches_unfused(cuda, kp_impl, deform):
         res.append((out.detach(), x.grad, b.grad, m.weights.grad.clone()))
     for a, r in zip(res[1], res[0]):
         assert rel_err(a.cpu(), r.cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("nq,ns,H,cin,cout", [(200, 300, 35, 32, 32), (90, 120, 42, 64, 64), (64, 64, 48, 256, 128),
+                                              (300, 200, 40, 33, 64), (500, 100, 70, 16, 32), (40, 1, 5, 8, 32),
+                                              (50, 60, 9, 12, 256)])
+@pytest.mark.parametrize("idx_dtype", [torch.int64, torch.int32])
+def test_kpconv_backward_over_transposed_lists(cuda, nq, ns, H, cin, cout, idx_dtype):
+    """Atomic-free grad_x (gather over d3f_neighbors_transpose lists + GEMM with W^T) vs the CPU oracle and vs the
+    scatter path; in-degrees far above one 64-entry chunk are covered by (500, 100, 70) and (40, 1, 5)."""
+    from oracle import model_ref
+    from d3feat.pytorch_b200 import ops
+    from d3feat.pytorch_b200.blocks import _KPConvFunction
+    rng = np.random.default_rng(nq * 31 + H)
+    q = torch.from_numpy((rng.random((nq, 3)) * 0.2).astype(np.float32))
+    s = torch.from_numpy((rng.random((ns, 3)) * 0.2).astype(np.float32))
+    inds = torch.from_numpy(rng.integers(0, ns + 1, size=(nq, H)).astype(np.int64))      # ns = shadow
+    x = torch.from_numpy(rng.standard_normal((ns, cin)).astype(np.float32)).requires_grad_(True)
+    W = torch.from_numpy((rng.standard_normal((15, cin, cout)) / np.sqrt(15 * cin)).astype(np.float32)).requires_grad_(True)
+    kp = torch.from_numpy((_inputs.unit_kernel_points() * 0.075).astype(np.float32))
+    gout = torch.from_numpy(rng.standard_normal((nq, cout)).astype(np.float32))
+    ref = model_ref.kpconv_rigid(q, s, inds, x, W, kp, 0.06)
+    (ref * gout).sum().backward()
+    inds_g = inds.to(cuda).to(idx_dtype)
+    t_off, t_src = ops.neighbors_transpose(inds_g, ns)
+    # the lists hold every (query, support) reference exactly once
+    off = t_off.cpu().numpy()
+    assert off[0] == 0 and off[-1] == int((inds < ns).sum())
+    counts = np.bincount(inds.numpy()[inds.numpy() < ns].ravel(), minlength=ns)
+    assert np.array_equal(np.diff(off), counts)
+    src = t_src.cpu().numpy()
+    for j in range(0, ns, max(1, ns // 7)):
+        assert sorted(src[off[j]:off[j + 1]].tolist()) == sorted(np.nonzero((inds.numpy() == j))[0].tolist())
+    grads = []
+    for tr in ((None, None), (t_off, t_src)):
+        xg = x.detach().to(cuda).requires_grad_(True)
+        Wg = W.detach().to(cuda).requires_grad_(True)
+        out, _ = _KPConvFunction.apply(q.to(cuda), s.to(cuda), inds_g, xg, Wg, kp.to(cuda), None, 0.06, "linear", "sum",
+                                       False, False, None, None, tr[0], tr[1])
+        (out * gout.to(cuda)).sum().backward()
+        grads.append((xg.grad.cpu(), Wg.grad.cpu()))
+    assert rel_err(grads[1][0], x.grad) < TOL and rel_err(grads[1][1], W.grad) < TOL
+    assert rel_err(grads[1][0], grads[0][0]) < 2e-5

@@ -70,11 +70,13 @@ for (M, N, K, ta, tb) in shapes:
     a = torch.randn((K, M) if ta else (M, K), device=dev)
     b = torch.randn((N, K) if tb else (K, N), device=dev)
     row = []
-    for pipe in (0, 1):
+    for pipe in (0, 1, 2):
         lib.d3f_set_gemm_pipeline(pipe)
         for det in (False, True):
             row.append(timed(lambda: ops.gemm(a, b, ta, tb, deterministic=det)))
     lib.d3f_set_gemm_pipeline(-1)
     fl = 2.0 * M * N * K
-    print("M=%6d N=%5d K=%6d ta=%d tb=%d | reg: %7.1f (det %7.1f) | cp.async: %7.1f (det %7.1f) | %.1f TFLOP/s best"
-          % (M, N, K, ta, tb, row[0], row[1], row[2], row[3], fl / min(row) / 1e6))
+    print("M=%6d N=%5d K=%6d ta=%d tb=%d | reg: %6.1f (det %6.1f) | cp.async: %6.1f (det %6.1f) | warp-spec: %6.1f (det %6.1f) | %.1f TFLOP/s best"
+          % (M, N, K, ta, tb, row[0], row[1], row[2], row[3], row[4], row[5], fl / min(row) / 1e6))
+if lib.d3f_gemm_tcgen05_failed() != 0:
+    print("WARNING: a tcgen05 GEMM gave up waiting on an mbarrier")
