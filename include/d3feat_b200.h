@@ -138,7 +138,8 @@ int d3f_kpconv_forward_ex(const float* q_pts, const float* s_pts, const void* in
  * exists for A/B measurements and parity tests. */
 void d3f_set_kpconv_impl(int impl);
 int d3f_get_kpconv_impl(void);
-/* v2 backward scatter: 1 = 128-bit vector reductions (red.global.add.v4.f32) where Cin allows it, 0 = scalar. */
+/* v2 backward scatter (the path without transposed lists): 1 = 128-bit vector reductions (red.global.add.v4.f32) for
+ * Cin % 128 == 0 (default), 2 = also for Cin = 32 / 64, 0 = scalar reductions only. */
 void d3f_set_scatter_vec(int use_vec);
 /* Measurement hook: cudaEvent_t handles (or NULL, NULL) recorded on the caller's stream right before and right after
  * the forward gather kernel of the next d3f_kpconv_forward calls, so that kernel can be timed alone. */

@@ -38,10 +38,14 @@ for name, lvl, kind, cin, cout in cases:
     W = torch.randn(15, cin, cout, device=dev) / (15 * cin) ** 0.5
     kpl = kp * (2 ** lvl)
     g = torch.randn(q.shape[0], cout, device=dev)
-    for impl, label, env in ((0, "v1", None), (1, "v2-ffma", None), (2, "v2-mma", None), (2, "v2-mma/scalar-red", "scalar")):
+    tr = ops.neighbors_transpose(inds, s.shape[0])
+    t_tr = timed(lambda: ops.neighbors_transpose(inds, s.shape[0]))
+    print("%-22s neighbors_transpose: %.1f us" % (name, t_tr))
+    for impl, label, env in ((0, "v1", None), (1, "v2-ffma", None), (2, "v2-mma", None), (2, "v2-mma/scalar-red", "scalar"),
+                             (2, "v2-mma/transposed", "t")):
         lib.d3f_set_kpconv_impl(impl)
         if hasattr(lib, "d3f_set_scatter_vec"):
-            lib.d3f_set_scatter_vec(0 if env == "scalar" else 1)
+            lib.d3f_set_scatter_vec(0 if env == "scalar" else 2)
         elif env == "scalar":
             continue
         ext = 0.8 * r
@@ -58,7 +62,7 @@ for name, lvl, kind, cin, cout in cases:
         t_g = ev[0].elapsed_time(ev[1]) * 1e3
         _, wf, wf_un, inv_n, _ = out
         t_b = timed(lambda: ops.kpconv_backward(q, s, inds, x, W, kpl, ext, "linear", "sum", False, None, wf, wf_un, inv_n, g,
-                                                cin > 1, True, False, False))
+                                                cin > 1, True, False, False, transpose=tr if env == "t" else None))
         print("%-22s %-18s %10.1f %10.1f %10.1f" % (name, label, t_g, t_f, t_b))
 lib.d3f_set_kpconv_impl(-1)
 

@@ -16,7 +16,6 @@ torch.cuda.set_device(0); dev = torch.device("cuda:0")
 cfg = default_config(); torch.manual_seed(0); np.random.seed(0)
 model = KPFCNN(cfg).to(dev); model.train()
 opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.98, weight_decay=1e-6)
-flat = parallel.FlatGradients(model)
 pairs = [synthetic.fragment_pair(n, seed=i) for i in range(2)]
 class DS:
     config = cfg
@@ -24,7 +23,7 @@ class DS:
     def __getitem__(self, i): return pairs[i]
 limits = [int(v) for v in calibrate_neighbors(DS(), cfg, collate_fn_descriptor, samples_threshold=10 ** 9)]
 sizes = [[int(t.shape[0]) for t in collate_fn_descriptor([p], cfg, limits)["points"]] for p in pairs]
-st = PairStep(model, cfg, limits, plan_capacities(sizes), n, n, PairLoss("circle"), opt, flat)
+st = PairStep(model, cfg, limits, plan_capacities(sizes), n, n, PairLoss("circle"), opt, None)
 st(pairs[0]); st.capture()
 for i in range(3): st(pairs[i % 2])
 torch.cuda.synchronize()
