@@ -56,9 +56,9 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t 
         :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* fail) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* fail, long long max_spin = (1LL << 26)) {
     uint32_t done = 0;
-    for (long long spin = 0; spin < (1LL << 26); ++spin) {
+    for (long long spin = 0; spin < max_spin; ++spin) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) return;
@@ -604,7 +604,7 @@ tc7_gemm_kernel(D3fGemm g) {
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
         for (int kt = 0; kt < nk; ++kt) {
             const int s = kt & 1;
-            mbar_wait(smem_u32(&bars[s]), (kt >> 1) & 1, &g_tc5_fail);          // all 8 converter warps filled stage s
+            mbar_wait(smem_u32(&bars[s]), (kt >> 1) & 1, &g_tc5_fail, 1LL << 18);          // all 8 converter warps filled stage s
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             if (lane == 0) {
                 const uint32_t a_hi = smem_u32(smem) + s * STAGE_BYTES, a_lo = a_hi + A_TILE;
@@ -700,7 +700,7 @@ tc7_gemm_kernel(D3fGemm g) {
         // one tile: wait until the MMAs that read stage s two tiles ago are done, fill it, prefetch tile kt + 2, signal
         auto step = [&](int kt, float4 (&a)[4], float4 (&b)[BN >= 128 ? BN / 32 : 4]) {
             const int s = kt & 1;
-            if (kt >= NS7) mbar_wait(smem_u32(&bars[2 + s]), ((kt >> 1) - 1) & 1, &g_tc5_fail);
+            if (kt >= NS7) mbar_wait(smem_u32(&bars[2 + s]), ((kt >> 1) - 1) & 1, &g_tc5_fail, 1LL << 18);
             store_tile(s, a, b);
             if (kt + 2 < nk) load_tile(kt + 2, a, b);
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");    // this thread's stores -> async proxy (UMMA)
@@ -714,7 +714,7 @@ tc7_gemm_kernel(D3fGemm g) {
             if (kt + 1 < nk) step(kt + 1, ra[1], rb[1]);
         }
         // every MMA has completed once the commit of the last tile has arrived
-        if (nk > 0) mbar_wait(smem_u32(&bars[2 + ((nk - 1) & 1)]), ((nk - 1) >> 1) & 1, &g_tc5_fail);
+        if (nk > 0) mbar_wait(smem_u32(&bars[2 + ((nk - 1) & 1)]), ((nk - 1) >> 1) & 1, &g_tc5_fail, 1LL << 18);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     }
 
