@@ -46,6 +46,7 @@ SIGNATURES = {
     "d3f_kpconv_set_gather_events": (None, [c_p, c_p]),
     "d3f_set_scatter_vec": (None, [c_i]),
     "d3f_colsum": (c_i, [c_p, c_i, c_i, c_p, c_p]),
+    "d3f_leaky_backward_colsum": (c_i, [c_p, c_p, c_f, c_i, c_i, c_p, c_p, c_p]),
     "d3f_max_pool_forward": (c_i, [c_p, c_p, c_i, c_i64, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "d3f_max_pool_backward": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
     "d3f_gather_rows_forward": (c_i, [c_p, c_p, c_i, c_i64, c_i, c_i, c_i, c_p, c_p]),

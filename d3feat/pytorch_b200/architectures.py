@@ -73,4 +73,7 @@ class KPFCNN(nn.Module):
         """Saliency x channel-max keypoint score (architectures.py:322-368): neighbour-mean saliency
         softplus(f - mean_nb f), depth-wise ratio f / max_c f, max over channels, and at test time the
         exact-equality local-max gate.  One fused warp-per-point kernel (d3f_detection_scores_*)."""
+        pyr = inputs.get('_pyramid') if isinstance(inputs, dict) else None
+        if pyr is not None:   # engine.collate_static builds the pyramid on side streams
+            pyr.wait(('neighbors', 0))
         return ops.detection_scores(features, inputs['neighbors'][0], not self.training)

@@ -67,9 +67,11 @@ class _KPConvFunction(torch.autograd.Function):
         q_pts, s_pts, inds, x, weights, kpoints, modulations, wf, wf_un, inv_n, out = ctx.saved_tensors
         extent, influence, aggregation, deformed, slope = ctx.cfg
         need = ctx.needs_input_grad
+        want_gb = len(need) > 12 and need[12]
         if slope is not None:   # out = leaky(z) has the sign of z: the mask comes from the saved output
-            grad_out = torch.ops.aten.leaky_relu_backward(grad_out.contiguous(), out, float(slope), True)
-        gbias = ops.colsum(grad_out) if (len(need) > 12 and need[12]) else None
+            grad_out, gbias = ops.leaky_backward_colsum(grad_out, out, slope, want_gb)
+        else:
+            gbias = ops.colsum(grad_out) if want_gb else None
         gx, gw, gkp, gmod = ops.kpconv_backward(
             q_pts.float().contiguous(), s_pts.float().contiguous(),
             inds if inds.dtype in (torch.int32, torch.int64) else inds.long(),
@@ -239,8 +241,17 @@ def _conv_geometry(block_name, layer_ind, batch):
     """(queries, supports, neighbour matrix) a conv block reads from the collate dict
     (blocks.py:588-595, :660-667): strided blocks go from layer l to l+1 through `pools`."""
     if 'strided' in block_name:
+        _ready(batch, ('points', layer_ind), ('points', layer_ind + 1), ('pools', layer_ind))
         return batch['points'][layer_ind + 1], batch['points'][layer_ind], batch['pools'][layer_ind]
+    _ready(batch, ('points', layer_ind), ('neighbors', layer_ind))
     return batch['points'][layer_ind], batch['points'][layer_ind], batch['neighbors'][layer_ind]
+
+
+def _ready(batch, *keys):
+    """engine.collate_static builds the pyramid on side streams: wait (on the current stream) for the named levels."""
+    pyr = batch.get('_pyramid') if isinstance(batch, dict) else None
+    if pyr is not None:
+        pyr.wait(*keys)
 
 
 def _make_kpconv(block_name, in_dim, out_dim, radius, config):
@@ -316,6 +327,7 @@ class NearestUpsampleBlock(nn.Module):
         self.layer_ind = layer_ind
 
     def forward(self, x, batch):
+        _ready(batch, ('upsamples', self.layer_ind - 1))
         return closest_pool(x, batch['upsamples'][self.layer_ind - 1])
 
     def __repr__(self):
@@ -328,6 +340,7 @@ class MaxPoolBlock(nn.Module):
         self.layer_ind = layer_ind
 
     def forward(self, x, batch):
+        _ready(batch, ('pools', self.layer_ind + 1))
         return max_pool(x, batch['pools'][self.layer_ind + 1])
 
 

@@ -260,25 +260,38 @@ __global__ void colsum_kernel(const float* __restrict__ x, int M, int N, int row
 // columns], so a warp reads 512 contiguous bytes per load and every lane is busy even at N = 32 (the scalar kernel
 // above keeps 32 of 128 threads busy there: 25 us for 5 MB in the round-1d profile); 4 independent loads in flight per
 // thread, a shared-memory reduction over the R row groups, one atomicAdd per column per CTA.
+// FUSE: x is the incoming gradient; dz = x * (y > 0 ? 1 : slope) is written out and its columns are summed (LeakyReLU
+// backward + bias gradient of the fused blocks in one pass over the gradient).
+template <bool FUSE>
 __global__ void __launch_bounds__(256)
-colsum_vec_kernel(const float4* __restrict__ x, int M, int nv, int nv_cta, int rows_per_cta, float* __restrict__ out) {
+colsum_vec_kernel(const float4* __restrict__ x, int M, int nv, int nv_cta, int rows_per_cta, float* __restrict__ out,
+                  const float4* __restrict__ y, float slope, float4* __restrict__ dz) {
     __shared__ float4 red[256];
     const int tid = threadIdx.x;
     const int cv = tid % nv_cta, rsub = tid / nv_cta, R = 256 / nv_cta;
     const int col = blockIdx.x * nv_cta + cv;                     // float4 column
     const int m0 = blockIdx.y * rows_per_cta, m1 = min(M, m0 + rows_per_cta);
+    auto ld = [&](int m) {
+        float4 v = x[(size_t)m * nv + col];
+        if (FUSE) {
+            const float4 r = y[(size_t)m * nv + col];
+            v.x *= r.x > 0.f ? 1.0f : slope; v.y *= r.y > 0.f ? 1.0f : slope;
+            v.z *= r.z > 0.f ? 1.0f : slope; v.w *= r.w > 0.f ? 1.0f : slope;
+            dz[(size_t)m * nv + col] = v;
+        }
+        return v;
+    };
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
     int m = m0 + rsub;
     for (; m + 3 * R < m1; m += 4 * R) {
-        const float4 v0 = x[(size_t)m * nv + col], v1 = x[(size_t)(m + R) * nv + col];
-        const float4 v2 = x[(size_t)(m + 2 * R) * nv + col], v3 = x[(size_t)(m + 3 * R) * nv + col];
+        const float4 v0 = ld(m), v1 = ld(m + R), v2 = ld(m + 2 * R), v3 = ld(m + 3 * R);
         a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
         a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
         a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
         a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
     }
     for (; m < m1; m += R) {
-        const float4 v0 = x[(size_t)m * nv + col];
+        const float4 v0 = ld(m);
         a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
     }
     red[tid] = make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y),
@@ -295,6 +308,21 @@ colsum_vec_kernel(const float4* __restrict__ x, int M, int nv, int nv_cta, int r
     }
 }
 
+// shared launch geometry of the vector kernels; false if the shape needs the scalar path
+static bool colsum_vec_geometry(int n_rows, int n_cols, dim3* grid, int* nv, int* nv_cta, int* rpc) {
+    *nv = n_cols / 4;
+    if ((n_cols & 3) != 0 || (*nv & (*nv - 1)) != 0) return false;
+    *nv_cta = *nv < 256 ? *nv : 256;
+    const int R = 256 / *nv_cta, col_ctas = *nv / *nv_cta;
+    int row_ctas = d3f_ceil_div(444, col_ctas);              // ~3 CTAs per SM
+    *rpc = d3f_ceil_div(n_rows, row_ctas);
+    if (*rpc < 8 * R) *rpc = 8 * R;
+    *rpc = d3f_ceil_div(*rpc, R) * R;
+    row_ctas = d3f_ceil_div(n_rows, *rpc);
+    *grid = dim3(col_ctas, row_ctas);
+    return true;
+}
+
 }  // namespace
 
 extern "C" int d3f_colsum(const float* x, int n_rows, int n_cols, float* out, d3f_stream stream_) {
@@ -303,16 +331,10 @@ extern "C" int d3f_colsum(const float* x, int n_rows, int n_cols, float* out, d3
     D3F_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * n_cols, stream));
     if (n_rows == 0) return D3F_OK;
     D3F_REQUIRE(x, D3F_ERR_INVALID, "null pointer");
-    const int nv = n_cols / 4;
-    if ((n_cols & 3) == 0 && (nv & (nv - 1)) == 0 && (((size_t)x) & 15) == 0) {
-        const int nv_cta = nv < 256 ? nv : 256, R = 256 / nv_cta;
-        const int col_ctas = nv / nv_cta;
-        int row_ctas = d3f_ceil_div(444, col_ctas);              // ~3 CTAs per SM
-        int rpc = d3f_ceil_div(n_rows, row_ctas);
-        if (rpc < 8 * R) rpc = 8 * R;
-        rpc = d3f_ceil_div(rpc, R) * R;
-        row_ctas = d3f_ceil_div(n_rows, rpc);
-        colsum_vec_kernel<<<dim3(col_ctas, row_ctas), 256, 0, stream>>>((const float4*)x, n_rows, nv, nv_cta, rpc, out);
+    dim3 grid;
+    int nv, nv_cta, rpc;
+    if ((((size_t)x) & 15) == 0 && colsum_vec_geometry(n_rows, n_cols, &grid, &nv, &nv_cta, &rpc)) {
+        colsum_vec_kernel<false><<<grid, 256, 0, stream>>>((const float4*)x, n_rows, nv, nv_cta, rpc, out, nullptr, 0.f, nullptr);
         D3F_CHECK_LAUNCH();
         return D3F_OK;
     }
@@ -322,6 +344,26 @@ extern "C" int d3f_colsum(const float* x, int n_rows, int n_cols, float* out, d3
     if (rpc < 32) rpc = 32;
     row_ctas = d3f_ceil_div(n_rows, rpc);
     colsum_kernel<<<dim3(col_ctas, row_ctas), 128, 0, stream>>>(x, n_rows, n_cols, rpc, out);
+    D3F_CHECK_LAUNCH();
+    return D3F_OK;
+}
+
+// dz = grad * (y > 0 ? 1 : slope) and colsum[n] = sum_m dz[m, n] in one pass (y = the saved LeakyReLU OUTPUT).
+// Returns D3F_ERR_UNSUPPORTED for shapes the vector kernel does not take (n_cols must be 4 * 2^j, 16-byte aligned rows);
+// the caller then uses the two separate ops.
+extern "C" int d3f_leaky_backward_colsum(const float* grad, const float* y, float slope, int n_rows, int n_cols, float* dz,
+                                         float* colsum, d3f_stream stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    D3F_REQUIRE(n_rows >= 0 && n_cols >= 1 && colsum, D3F_ERR_INVALID, "bad arguments");
+    dim3 grid;
+    int nv, nv_cta, rpc;
+    if ((((size_t)grad | (size_t)y | (size_t)dz) & 15) != 0 || !colsum_vec_geometry(n_rows, n_cols, &grid, &nv, &nv_cta, &rpc))
+        return D3F_ERR_UNSUPPORTED;
+    D3F_CHECK_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * n_cols, stream));
+    if (n_rows == 0) return D3F_OK;
+    D3F_REQUIRE(grad && y && dz, D3F_ERR_INVALID, "null pointer");
+    colsum_vec_kernel<true><<<grid, 256, 0, stream>>>((const float4*)grad, n_rows, nv, nv_cta, rpc, colsum, (const float4*)y,
+                                                     slope, (float4*)dz);
     D3F_CHECK_LAUNCH();
     return D3F_OK;
 }

@@ -54,16 +54,45 @@ def _pyramid_levels(config):
     return levels
 
 
-def collate_static(pts0, pts1, feat0, feat1, corr, dist_keypts, config, limits, caps, lengths=None, side_stream=None,
-                   transposes=False):
-    """Same pyramid as dataloader.collate_fn_descriptor (reference dataloader.py:69-189) on
-    capacity-padded tensors, with no host synchronisation.  Returns (batch dict, status int32 tensor);
-    status must be all zeros for the batch to be valid (checked by the caller after the step).
+class _Pyramid:
+    """Hand-over between the pyramid build (side streams) and its consumers (the model on the current stream)."""
 
-    The grid-subsampling chain (level l+1 needs level l only) and the radius searches are independent until a
-    pool / upsample search needs the next level's points: with `side_stream` the chain runs there (its order
-    kernel is one CTA per cloud, ~125 us per level with 146 SMs idle) while the searches fill the GPU on the
-    current stream; events order the two.  Inside a CUDA-graph capture this becomes a fork/join in the graph."""
+    def __init__(self, main, streams):
+        self.main, self.streams, self.events, self.flags = main, [st for st in streams if st is not None], {}, []
+
+    def mark(self, key, stream):
+        if stream is not None:
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            self.events[key] = ev
+
+    def wait(self, *keys):
+        """Make the CURRENT stream wait until the tensors named by `keys` have been produced."""
+        cur = torch.cuda.current_stream()
+        for key in keys:
+            ev = self.events.get(key)
+            if ev is not None:
+                cur.wait_event(ev)
+
+    def join(self):
+        """Close the fork (every side stream back into the main stream) and return the status vector."""
+        for st in self.streams:
+            self.main.wait_stream(st)
+        return torch.cat(self.flags)
+
+
+def collate_static(pts0, pts1, feat0, feat1, corr, dist_keypts, config, limits, caps, lengths=None, side_stream=None,
+                   transposes=False, search_stream=None):
+    """Same pyramid as dataloader.collate_fn_descriptor (reference dataloader.py:69-189) on capacity-padded tensors,
+    with no host synchronisation.  Returns (batch dict, pyramid); `pyramid.join()` gives the status int32 tensor, which
+    must be all zeros for the batch to be valid (checked by the caller after the step).
+
+    Streams.  The grid-subsampling chain (level l+1 needs level l only; its order kernel is one CTA per cloud, ~130 us
+    per level with 146 SMs idle) runs on `side_stream`, the radius searches (+ transposed lists) on `search_stream`,
+    and the CONSUMER -- the network on the current stream -- waits per tensor (batch['_pyramid'].wait(('neighbors', l))
+    in blocks._conv_geometry etc.), so the level-0 convolutions start as soon as the level-0 search is done while the
+    deeper levels are still being built.  Inside a CUDA-graph capture this becomes a fork/join in the graph.  With both
+    streams None everything runs in order on the current stream."""
     dev = pts0.device
     points = torch.cat([pts0, pts1], dim=0)
     feats = torch.cat([feat0, feat1], dim=0)
@@ -71,15 +100,18 @@ def collate_static(pts0, pts1, feat0, feat1, corr, dist_keypts, config, limits, 
         lengths = torch.tensor([pts0.shape[0], pts1.shape[0]], dtype=torch.int32, device=dev)
     levels = _pyramid_levels(config)
     out = {'points': [], 'neighbors': [], 'pools': [], 'upsamples': [], 'stack_lengths': []}
-    flags = []
     empty_idx = torch.zeros((0, 1), dtype=torch.int32, device=dev)
 
-    # ---- subsampling chain (side stream when given)
     main = torch.cuda.current_stream()
-    pts, lens, ready = [points], [lengths], [None]
-    if side_stream is not None:
-        side_stream.wait_stream(main)
-    with torch.cuda.stream(side_stream if side_stream is not None else main):
+    pyr = _Pyramid(main, [side_stream, search_stream])
+    flags = pyr.flags
+    for st in pyr.streams:
+        st.wait_stream(main)             # fork: the inputs were written on the main stream
+
+    # ---- subsampling chain
+    sub_s = side_stream if side_stream is not None else main
+    pts, lens = [points], [lengths]
+    with torch.cuda.stream(sub_s):
         r_normal = config.first_subsampling_dl * config.conv_radius
         for l, (_, _, has_pool, _) in enumerate(levels):
             if has_pool:
@@ -89,16 +121,10 @@ def collate_static(pts0, pts1, feat0, feat1, corr, dist_keypts, config, limits, 
                 flags.append((pool_len[:2] < 0).to(torch.int32))  # unsupported voxel grid
                 pts.append(pool_p)
                 lens.append(pool_len[:2])
-                if side_stream is not None:
-                    ev = torch.cuda.Event()
-                    ev.record(side_stream)
-                    ready.append(ev)
-                else:
-                    ready.append(None)
+                pyr.mark(('points', l + 1), side_stream)
             else:
                 pts.append(torch.zeros((0, 3), dtype=torch.float32, device=dev))
                 lens.append(torch.zeros((0,), dtype=torch.int32, device=dev))
-                ready.append(None)
             r_normal *= 2
 
     def search(q, s, ql, sl, r, limit, pad, transpose=False):
@@ -111,35 +137,41 @@ def collate_static(pts0, pts1, feat0, feat1, corr, dist_keypts, config, limits, 
         idx._d3f_width = torch.clamp(info[0:1], max=int(limit))
         return idx
 
-    # ---- radius searches (current stream)
-    r_normal = config.first_subsampling_dl * config.conv_radius
-    for l, (has_conv, deform_conv, has_pool, deform_pool) in enumerate(levels):
-        cap = caps[l]
-        if has_conv:
-            r = r_normal * config.deform_radius / config.conv_radius if deform_conv else r_normal
-            conv_i = search(pts[l], pts[l], lens[l], lens[l], r, limits[l], cap, transposes and not deform_conv)
-        else:
-            conv_i = empty_idx
-        if has_pool:
-            if ready[l + 1] is not None:
-                main.wait_event(ready[l + 1])
-            r = r_normal * config.deform_radius / config.conv_radius if deform_pool else r_normal
-            pool_i = search(pts[l + 1], pts[l], lens[l + 1], lens[l], r, limits[l], cap, transposes and not deform_pool)
-            up_i = search(pts[l], pts[l + 1], lens[l], lens[l + 1], 2 * r, limits[l], caps[l + 1])
-        else:
-            pool_i, up_i = empty_idx, empty_idx
-        out['points'].append(pts[l])
-        out['neighbors'].append(conv_i)
-        out['pools'].append(pool_i)
-        out['upsamples'].append(up_i)
-        out['stack_lengths'].append(lens[l])
-        r_normal *= 2
-    if side_stream is not None:
-        main.wait_stream(side_stream)   # join (all events above were already waited on; this closes the fork)
+    # ---- radius searches
+    srch_s = search_stream if search_stream is not None else main
+    with torch.cuda.stream(srch_s):
+        r_normal = config.first_subsampling_dl * config.conv_radius
+        for l, (has_conv, deform_conv, has_pool, deform_pool) in enumerate(levels):
+            cap = caps[l]
+            pyr.wait(('points', l))                      # (no-op for level 0 and without a side stream)
+            if has_conv:
+                r = r_normal * config.deform_radius / config.conv_radius if deform_conv else r_normal
+                conv_i = search(pts[l], pts[l], lens[l], lens[l], r, limits[l], cap, transposes and not deform_conv)
+                pyr.mark(('neighbors', l), search_stream)
+            else:
+                conv_i = empty_idx
+            if has_pool:
+                pyr.wait(('points', l + 1))
+                r = r_normal * config.deform_radius / config.conv_radius if deform_pool else r_normal
+                pool_i = search(pts[l + 1], pts[l], lens[l + 1], lens[l], r, limits[l], cap, transposes and not deform_pool)
+                pyr.mark(('pools', l), search_stream)
+                up_i = search(pts[l], pts[l + 1], lens[l], lens[l + 1], 2 * r, limits[l], caps[l + 1])
+                pyr.mark(('upsamples', l), search_stream)
+            else:
+                pool_i, up_i = empty_idx, empty_idx
+            out['points'].append(pts[l])
+            out['neighbors'].append(conv_i)
+            out['pools'].append(pool_i)
+            out['upsamples'].append(up_i)
+            out['stack_lengths'].append(lens[l])
+            r_normal *= 2
+    if search_stream is None and side_stream is not None:
+        main.wait_stream(side_stream)    # searches ran on the main stream: everything the consumer needs is ordered
     out['features'] = feats
     out['corr'] = corr
     out['dist_keypts'] = dist_keypts
-    return out, torch.cat(flags)
+    out['_pyramid'] = pyr
+    return out, pyr
 
 
 class PairStep:
@@ -170,14 +202,17 @@ class PairStep:
         self.det_loss = torch.zeros((), **f32)
         self.status = None
         self.batch = None
-        self.side_stream = torch.cuda.Stream(device=dev)   # grid-subsampling chain, concurrent with the radius searches
+        self.side_stream = torch.cuda.Stream(device=dev)     # grid-subsampling chain
+        self.search_stream = torch.cuda.Stream(device=dev)   # radius searches + transposed lists; the network consumes
+                                                             # each level as soon as it is ready (see collate_static)
 
     # -- the step on the static input buffers
     def _body(self):
         cfg = self.config
-        batch, status = collate_static(*self.inputs, cfg, self.limits, self.caps, self.lengths0, self.side_stream,
-                                       transposes=self.optimizer is not None)
+        batch, pyramid = collate_static(*self.inputs, cfg, self.limits, self.caps, self.lengths0, self.side_stream,
+                                        transposes=self.optimizer is not None, search_stream=self.search_stream)
         feats, scores = self.model(batch)
+        status = pyramid.join()          # the backward pass reads the transposed lists built on the search stream
         c = batch['corr']
         ia, ip = c[:, 0], c[:, 1] + self.n0
         a, p = gather(feats, ia), gather(feats, ip)            # trainer.py:91-94

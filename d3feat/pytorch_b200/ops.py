@@ -483,6 +483,24 @@ def colsum(x):
     return out
 
 
+def leaky_backward_colsum(gy, y, slope, want_colsum=True):
+    """(dz, colsum(dz)) with dz = gy * (y > 0 ? 1 : slope), y = the saved LeakyReLU output: one kernel
+    (d3f_leaky_backward_colsum) where the channel count allows it, else ATen's leaky_relu_backward + d3f_colsum."""
+    lib = _lib.load()
+    gy, y = _cuda_f32(gy, "grad"), _cuda_f32(y, "y")
+    M, N = gy.shape
+    if want_colsum:
+        dz = torch.empty_like(gy)
+        db = torch.empty(N, dtype=torch.float32, device=gy.device)
+        rc = lib.d3f_leaky_backward_colsum(_p(gy), _p(y), float(slope), M, N, _p(dz), _p(db), _stream())
+        if rc == 0:
+            return dz, db
+        if rc != -4:   # D3F_ERR_UNSUPPORTED: shape not covered by the vector kernel
+            _lib.check(rc)
+    dz = torch.ops.aten.leaky_relu_backward(gy, y, float(slope), True).contiguous()
+    return dz, (colsum(dz) if want_colsum else None)
+
+
 class _FusedLinear(torch.autograd.Function):
     """y = LeakyReLU_slope(x @ W^T + b + b2 + residual)  (slope None: no activation; b2 / residual optional) -- the
     UnaryBlock body (models/blocks.py:505-510 with use_bn=False: Linear bias + learned bias) and, with `residual`, the
@@ -498,13 +516,15 @@ class _FusedLinear(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         x, weight, y = ctx.saved_tensors
-        # y = leaky(z) has the sign of z (slope > 0), so the mask can be taken from the saved output: one kernel
-        dz = gy if y is None else torch.ops.aten.leaky_relu_backward(gy, y, float(ctx.slope), True)
-        dz = dz.contiguous()
         need = ctx.needs_input_grad
+        want_db = need[2] or need[3]
+        if y is None:
+            dz = gy.contiguous()
+            db = colsum(dz) if want_db else None
+        else:   # y = leaky(z) has the sign of z (slope > 0): the mask comes from the saved output, fused with the bias grad
+            dz, db = leaky_backward_colsum(gy, y, ctx.slope, want_db)
         dx = gemm(dz, weight) if need[0] else None                 # [M,out] @ [out,in]
         dw = gemm(dz, x, trans_a=True) if need[1] else None         # dz^T [out,M] @ x [M,in]
-        db = colsum(dz) if (need[2] or need[3]) else None
         return dx, dw, db if need[2] else None, db if need[3] else None, dz if need[4] else None, None
 
 

@@ -233,6 +233,10 @@ int d3f_pair_loss_backward(const float* anchor, const float* positive, int P, in
  */
 /* out[n] = sum over rows of x[n_rows, n_cols] (bias gradients of the fused UnaryBlock) */
 int d3f_colsum(const float* x, int n_rows, int n_cols, float* out, d3f_stream stream);
+/* LeakyReLU backward fused with the bias gradient: dz = grad * (y > 0 ? 1 : slope) with y the saved activation OUTPUT,
+ * colsum[n] = sum_m dz[m, n].  n_cols must be 4 * 2^j with 16-byte aligned buffers, else D3F_ERR_UNSUPPORTED. */
+int d3f_leaky_backward_colsum(const float* grad, const float* y, float slope, int n_rows, int n_cols, float* dz,
+                              float* colsum, d3f_stream stream);
 int d3f_max_pool_forward(const float* x, const void* inds, int idx_is_64, int64_t ld_inds, int n_queries,
                          int n_supports, int n_neighbors, int channels, const int32_t* valid_width, float* out,
                          int32_t* argmax, d3f_stream stream);

@@ -32,7 +32,8 @@ def test_collate_static_matches_exact_pyramid(cuda):
     sizes = [int(p.shape[0]) for p in exact["points"]]
     caps = plan_capacities([sizes], margin=1.25, align=32)
     dev = [torch.as_tensor(a).to(cuda) for a in data]
-    batch, status = collate_static(*dev, cfg, limits, caps)
+    batch, pyramid = collate_static(*dev, cfg, limits, caps)
+    status = pyramid.join()
     assert int(status.abs().sum()) == 0
     for l, n in enumerate(sizes):
         assert batch["points"][l].shape[0] == caps[l]
@@ -50,6 +51,28 @@ def test_collate_static_matches_exact_pyramid(cuda):
             assert torch.equal(got, want), (key, l)
             assert bool((s[:rows, w:] == cap_sup).all()) and bool((s[rows:] == cap_sup).all())
         assert batch["stack_lengths"][l].tolist() == exact["stack_lengths"][l].tolist()
+
+
+def test_collate_static_side_streams_same_pyramid(cuda):
+    """Subsampling chain and searches on side streams + transposed lists: same tensors as the in-order build."""
+    from d3feat.pytorch_b200.engine import collate_static, plan_capacities
+    cfg, limits, _ = _setup(cuda)
+    data = synthetic.fragment_pair(1500, seed=6, num_node=64)
+    dev = [torch.as_tensor(a).to(cuda) for a in data]
+    ref, pyr = collate_static(*dev, cfg, limits, [3000, 1280, 384, 128, 64])
+    pyr.join()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    got, pyr2 = collate_static(*dev, cfg, limits, [3000, 1280, 384, 128, 64], side_stream=s1, transposes=True, search_stream=s2)
+    status = pyr2.join()
+    torch.cuda.synchronize()
+    assert int(status.abs().sum()) == 0
+    for key in ("points", "neighbors", "pools", "upsamples", "stack_lengths"):
+        for a, b in zip(ref[key], got[key]):
+            assert torch.equal(a, b), key
+    for l, m in enumerate(got["neighbors"]):
+        t_off, t_src = m._d3f_transpose
+        ns = got["points"][l].shape[0]
+        assert int(t_off[-1]) == int((m < ns).sum()) and int(t_off[0]) == 0
 
 
 @pytest.mark.parametrize("deform", [False, True])

@@ -122,3 +122,15 @@ def test_colsum(cuda, M, N):
     ref = x.double().sum(0)
     got = ops.colsum(x)
     assert float((got.double() - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("M,N", [(40000, 32), (2816, 128), (5, 2048), (1000, 40), (333, 64)])
+def test_leaky_backward_colsum(cuda, M, N):
+    from d3feat.pytorch_b200 import ops
+    rng = np.random.default_rng(M * 3 + N)
+    g = torch.from_numpy(rng.standard_normal((M, N)).astype(np.float32)).to(cuda)
+    y = torch.from_numpy(rng.standard_normal((M, N)).astype(np.float32)).to(cuda)
+    dz, db = ops.leaky_backward_colsum(g, y, 0.1)
+    ref = g * torch.where(y > 0, 1.0, 0.1)
+    assert torch.equal(dz, ref)
+    assert float((db.double() - ref.double().sum(0)).abs().max()) < 2e-5 * max(1.0, float(ref.double().sum(0).abs().max()))

@@ -33,7 +33,8 @@ exact = collate_fn_descriptor([data], cfg, limits)
 sizes = [int(p.shape[0]) for p in exact["points"]]
 g_a = run(exact); g_a2 = run(exact)
 caps = plan_capacities([sizes], margin=1.2, align=32)
-static, status = collate_static(*[torch.as_tensor(a).to(dev) for a in data], cfg, limits, caps)
+static, _pyr = collate_static(*[torch.as_tensor(a).to(dev) for a in data], cfg, limits, caps)
+status = _pyr.join()
 g_b = run(static); g_b2 = run(static)
 for h in hs: h.remove()
 lvl_of = {}

@@ -15,7 +15,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 torch.cuda.set_device(0); dev = torch.device("cuda:0")
 cfg = default_config(); torch.manual_seed(0); np.random.seed(0)
 model = KPFCNN(cfg).to(dev); model.train()
-opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.98, weight_decay=1e-6)
+opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.98, weight_decay=1e-6, fused=True)
 pairs = [synthetic.fragment_pair(n, seed=i) for i in range(2)]
 class DS:
     config = cfg
