@@ -340,7 +340,7 @@ extern "C" int d3f_colsum(const float* x, int n_rows, int n_cols, float* out, d3
     }
     const int col_ctas = d3f_ceil_div(n_cols, 128);
     int row_ctas = d3f_ceil_div(592, col_ctas);                  // ~4 CTAs per SM
-    int rpc = d3f_ceil_div(n_rows, row_ctas);
+    rpc = d3f_ceil_div(n_rows, row_ctas);
     if (rpc < 32) rpc = 32;
     row_ctas = d3f_ceil_div(n_rows, rpc);
     colsum_kernel<<<dim3(col_ctas, row_ctas), 128, 0, stream>>>(x, n_rows, n_cols, rpc, out);
