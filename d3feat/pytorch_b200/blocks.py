@@ -72,12 +72,20 @@ class _KPConvFunction(torch.autograd.Function):
             grad_out, gbias = ops.leaky_backward_colsum(grad_out, out, slope, want_gb)
         else:
             gbias = ops.colsum(grad_out) if want_gb else None
-        gx, gw, gkp, gmod = ops.kpconv_backward(
-            q_pts.float().contiguous(), s_pts.float().contiguous(),
-            inds if inds.dtype in (torch.int32, torch.int64) else inds.long(),
-            x.float().contiguous(), weights.contiguous(), kpoints.float().contiguous(), extent, influence,
-            aggregation, deformed, modulations, wf, wf_un, inv_n, grad_out,
-            need_x=need[3], need_w=need[4], need_kp=need[5] and deformed, need_mod=need[6], transpose=ctx.transpose)
+        args = (q_pts.float().contiguous(), s_pts.float().contiguous(),
+                inds if inds.dtype in (torch.int32, torch.int64) else inds.long(),
+                x.float().contiguous(), weights.contiguous(), kpoints.float().contiguous(), extent, influence,
+                aggregation, deformed, modulations, wf, wf_un, inv_n, grad_out.contiguous())
+        need_data = need[3] or (need[5] and deformed) or need[6]
+        if need[4] and need_data:
+            # the weight gradient (one GEMM over wf) and the data-gradient chain are independent: two branches
+            (_, gw, _, _), (gx, _, gkp, gmod) = ops.run_branches(
+                lambda: ops.kpconv_backward(*args, need_x=False, need_w=True, need_kp=False, need_mod=False),
+                lambda: ops.kpconv_backward(*args, need_x=need[3], need_w=False, need_kp=need[5] and deformed,
+                                            need_mod=need[6], transpose=ctx.transpose), grad_out.device)
+        else:
+            gx, gw, gkp, gmod = ops.kpconv_backward(*args, need_x=need[3], need_w=need[4], need_kp=need[5] and deformed,
+                                                    need_mod=need[6], transpose=ctx.transpose)
         return (None, None, None, gx, gw, gkp, gmod, None, None, None, None, None, gbias, None, None, None)[:len(need)]
 
 

@@ -483,6 +483,37 @@ def colsum(x):
     return out
 
 
+# --------------------------------------------------------------------------- concurrent backward branches
+# The weight-gradient GEMM of a layer (dW = dz^T x, or wf^T g for KPConv) and its data-gradient chain are independent
+# and each is latency-bound on a few dozen CTAs: running the dW branch on an auxiliary stream lets them share the GPU.
+# Inside a CUDA-graph capture the fork/join becomes two parallel branches of the graph.  BRANCHES = False runs them in
+# order on the current stream.
+BRANCHES = True
+_AUX_STREAMS = {}
+
+
+def _aux_stream(device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    st = _AUX_STREAMS.get(key)
+    if st is None:
+        st = _AUX_STREAMS[key] = torch.cuda.Stream(device=key)
+    return st
+
+
+def run_branches(side_fn, main_fn, device):
+    """side_fn() on the auxiliary stream concurrently with main_fn() on the current stream; both have completed (in
+    stream order) when this returns.  Returns (side result, main result)."""
+    if not BRANCHES:
+        return side_fn(), main_fn()
+    cur, aux = torch.cuda.current_stream(), _aux_stream(device)
+    aux.wait_stream(cur)
+    with torch.cuda.stream(aux):
+        a = side_fn()
+    b = main_fn()
+    cur.wait_stream(aux)
+    return a, b
+
+
 def leaky_backward_colsum(gy, y, slope, want_colsum=True):
     """(dz, colsum(dz)) with dz = gy * (y > 0 ? 1 : slope), y = the saved LeakyReLU output: one kernel
     (d3f_leaky_backward_colsum) where the channel count allows it, else ATen's leaky_relu_backward + d3f_colsum."""
@@ -523,8 +554,12 @@ class _FusedLinear(torch.autograd.Function):
             db = colsum(dz) if want_db else None
         else:   # y = leaky(z) has the sign of z (slope > 0): the mask comes from the saved output, fused with the bias grad
             dz, db = leaky_backward_colsum(gy, y, ctx.slope, want_db)
-        dx = gemm(dz, weight) if need[0] else None                 # [M,out] @ [out,in]
-        dw = gemm(dz, x, trans_a=True) if need[1] else None         # dz^T [out,M] @ x [M,in]
+        if need[0] and need[1]:
+            dw, dx = run_branches(lambda: gemm(dz, x, trans_a=True),    # dz^T [out,M] @ x [M,in]
+                                  lambda: gemm(dz, weight), dz.device)  # [M,out] @ [out,in]
+        else:
+            dx = gemm(dz, weight) if need[0] else None
+            dw = gemm(dz, x, trans_a=True) if need[1] else None
         return dx, dw, db if need[2] else None, db if need[3] else None, dz if need[4] else None, None
 
 
