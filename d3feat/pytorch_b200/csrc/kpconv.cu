@@ -639,7 +639,11 @@ extern "C" int d3f_kpconv_backward_ex(const float* q_pts, const float* s_pts, co
     int rc = kp_check(nq, ns, H, K, cin, cout);
     if (rc) return rc;
     D3F_REQUIRE(influence >= 0 && influence <= 2 && aggregation >= 0 && aggregation <= 1, D3F_ERR_INVALID, "bad mode");
-    if (grad_x && ns > 0) D3F_CHECK_CUDA(cudaMemsetAsync(grad_x, 0, sizeof(float) * (size_t)ns * cin, stream));
+    const bool transposed = grad_x && t_offsets && t_src && !deformed && !modulations && kp_impl() >= 1 &&
+                            kp2t_supported(nq, cout) && ns > 0 && nq > 0;
+    // the scatter accumulates into grad_x with reductions; the transposed path's GEMM overwrites it
+    if (grad_x && ns > 0 && !transposed)
+        D3F_CHECK_CUDA(cudaMemsetAsync(grad_x, 0, sizeof(float) * (size_t)ns * cin, stream));
     if (nq == 0) {
         if (grad_weights) D3F_CHECK_CUDA(cudaMemsetAsync(grad_weights, 0, sizeof(float) * (size_t)K * cin * cout, stream));
         return D3F_OK;
@@ -658,7 +662,7 @@ extern "C" int d3f_kpconv_backward_ex(const float* q_pts, const float* s_pts, co
     }
     const bool need_scatter = grad_x || (deformed && (grad_kernel_points || grad_modulations));
     if (!need_scatter) return D3F_OK;
-    if (grad_x && t_offsets && t_src && !deformed && !modulations && kp_impl() >= 1 && kp2t_supported(nq, cout) && ns > 0) {
+    if (transposed) {
         // atomic-free: G[j,k,o] over the transposed lists, then grad_x[j,c] = sum_{k,o} G[j,k,o] W[k,c,o]
         float* G = w.dwf;
         Kp2tArgs ta{q_pts, s_pts, t_offsets, t_src, grad_out, inv_n, kernel_points, nq, ns, K, cout, kp_extent, influence,
