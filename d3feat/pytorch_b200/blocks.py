@@ -316,19 +316,12 @@ class ResnetBottleneckBlock(nn.Module):
         q_pts, s_pts, inds = _conv_geometry(self.block_name, self.layer_ind, batch)
         strided = 'strided' in self.block_name
         if not self.use_bn and features.is_cuda:
-            # conv + bias + LeakyReLU in one op; unary2 + shortcut add + LeakyReLU in one GEMM epilogue.  The shortcut
-            # (max-pool / Linear) only meets the main branch in that epilogue: it runs as a concurrent branch (autograd
-            # replays its backward on the same auxiliary stream).
-            def main_branch():
-                return self.KPConv(q_pts, s_pts, inds, self.unary1(features), bias=self.batch_norm_conv.bias, slope=0.1)
-
-            def shortcut_branch():
-                return self.unary_shortcut(max_pool(features, inds) if strided else features)
-
-            if ops.FORWARD_BRANCHES and (strided or not isinstance(self.unary_shortcut, nn.Identity)):
-                sc, x = ops.run_branches(shortcut_branch, main_branch, features.device)
-            else:
-                sc, x = shortcut_branch(), main_branch()
+            # conv + bias + LeakyReLU in one op; unary2 + shortcut add + LeakyReLU in one GEMM epilogue.
+            # (Running the shortcut as a concurrent forward branch was tried in round 1: autograd then replays its
+            # backward on the auxiliary stream, a parameter gradient was lost inside the CUDA-graph capture, and the
+            # step gained under 1 % -- the fork/join stays inside the backward nodes, see ops.run_branches.)
+            x = self.KPConv(q_pts, s_pts, inds, self.unary1(features), bias=self.batch_norm_conv.bias, slope=0.1)
+            sc = self.unary_shortcut(max_pool(features, inds) if strided else features)
             return self.unary2.forward_residual(x, sc, 0.1)
         shortcut = max_pool(features, inds) if strided else features
         x = self.KPConv(q_pts, s_pts, inds, self.unary1(features))

@@ -489,7 +489,6 @@ def colsum(x):
 # Inside a CUDA-graph capture the fork/join becomes two parallel branches of the graph.  BRANCHES = False runs them in
 # order on the current stream.
 BRANCHES = True
-FORWARD_BRANCHES = True      # ResnetBottleneckBlock: shortcut (max-pool / Linear) concurrent with unary1 -> KPConv
 _AUX_STREAMS = {}
 
 
