@@ -372,10 +372,19 @@ def run_b200(args):
     # separate pass with per-op CUDA events (same steps, same stream) for the roofline / op breakdown only
     _, _, _, prof = timed("device", args.steps, profile=True)
 
-    if rank != 0:
+    def finish():
+        """Leave without interpreter / NCCL teardown: with CUDA graphs that captured NCCL kernels,
+        destroy_process_group() (and the implicit teardown at exit) hung a 2-GPU run after its JSON line was out
+        (round 1).  All ranks meet at a barrier first so nobody exits under a peer that still needs it."""
         if world > 1:
-            dist.destroy_process_group()
-        return
+            dist.barrier()
+            torch.cuda.synchronize()
+        _REAL_STDOUT.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+    if rank != 0:
+        finish()
 
     if args.host_profile:
         n_calls = 2 * args.steps + args.steps
@@ -470,8 +479,7 @@ def run_b200(args):
                                           "in the reference; model+loss+bwd+SGD: torch-CPU oracle on %d threads = fastest of {8,16,32,64,all %d})" % (n_cpu, cores, os.cpu_count() or 1),
                                 "stage_seconds_per_pair": {k: v / n_cpu for k, v in stages.items()}}
     emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":
