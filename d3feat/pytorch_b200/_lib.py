@@ -63,6 +63,7 @@ SIGNATURES = {
     "d3f_kpconv_forward_ex": (c_i, [c_p, c_p, c_p, c_i, c_i64, c_p, c_p, c_p, c_i, c_p,
                                     c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_i, c_p, c_i, c_f,
                                     c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "d3f_mutual_nn": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
     "d3f_pair_loss_aux_floats": (c_sz, [c_i]),
     "d3f_pair_dist": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
     "d3f_pair_loss_forward": (c_i, [c_p, c_p, c_i, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_d, c_f, c_f, c_f,

@@ -310,6 +310,27 @@ def pair_loss_backward(saved, kind, metric, safe_radius, pos_margin, neg_margin,
     return ga, gp, gsa, gsp
 
 
+# --------------------------------------------------------------------------- mutual nearest-neighbour matching
+def mutual_nn(source, target):
+    """d3f_mutual_nn: (pairs [n,2] int32 ascending in source index, source_arg [Ns] int32, target_arg [Nt] int32) for
+    two descriptor sets on the GPU.  One D2H read of the pair count sizes the result, like the NumPy array the
+    reference builds (geometric_registration/common.py:5-21)."""
+    lib = _lib.load()
+    source, target = _cuda_f32(source, "source"), _cuda_f32(target, "target")
+    if source.dim() != 2 or target.dim() != 2 or source.shape[1] != target.shape[1]:
+        raise RuntimeError("mutual_nn: descriptors must be [N, D] and [M, D]")
+    ns, nt, d = source.shape[0], target.shape[0], source.shape[1]
+    dev = source.device
+    sarg = torch.empty(ns, dtype=torch.int32, device=dev)
+    targ = torch.empty(nt, dtype=torch.int32, device=dev)
+    pairs = torch.empty((max(ns, 1), 2), dtype=torch.int32, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    global launch_count
+    launch_count += 1
+    _lib.check(lib.d3f_mutual_nn(_p(source), _p(target), ns, nt, d, _p(sarg), _p(targ), _p(pairs), _p(count), _stream()))
+    return pairs[:int(count.item())], sarg, targ
+
+
 # --------------------------------------------------------------------------- pooling / gathers / detection scores
 def _idx(t, name):
     if not t.is_cuda:

@@ -255,6 +255,19 @@ int d3f_detection_scores_backward(const float* features, const void* neighbors, 
                                   float* grad_features, d3f_stream stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Mutual nearest-neighbour matching of two descriptor sets.  Replaces build_correspondence
+ * (geometric_registration/common.py:5-21; numpy on the host in the reference, called from evaluate.py per fragment pair):
+ *   distance = sqrt(2 - 2 * source @ target^T)   (fp32),
+ *   source_arg[i] = argmin_j distance[i, j],  target_arg[j] = argmin_i distance[i, j]   (numpy.argmin semantics: the
+ *   first NaN of a row / column wins -- 2 - 2<s,t> < 0 happens for descriptors a hair longer than 1 -- else the first
+ *   minimum),  pairs = [(i, source_arg[i]) : target_arg[source_arg[i]] == i] in ascending i.
+ *   source [n_source, dim], target [n_target, dim] f32;  source_arg [n_source], target_arg [n_target] i32 out;
+ *   pairs [min(n_source, n_target), 2] i32 out (capacity n_source rows is always enough);  n_pairs [1] i32 out (device).
+ */
+int d3f_mutual_nn(const float* source, const float* target, int n_source, int n_target, int dim,
+                  int32_t* source_arg, int32_t* target_arg, int32_t* pairs, int32_t* n_pairs, d3f_stream stream);
+
+/* ------------------------------------------------------------------------------------------
  * fp32-accurate tensor-core GEMM (3xTF32) with fused epilogue -- the dense contraction behind KPConv
  * (blocks.py:369-380) and the UnaryBlock Linear + bias + LeakyReLU (blocks.py:481-515):
  *   C[M,N] = act( row_scale[m] * sum_k opA(m,k) * k_scale[k] * opB(k,n) + bias[n] )

@@ -293,3 +293,17 @@ def pair_losses(features, scores, batch, desc="circle", **kw):
     fn = circle_loss if desc == "circle" else contrastive_loss
     dl, acc, fp, an, d = fn(a, p, batch["dist_keypts"], **kw)
     return dl, det_loss(d, sa, sp), acc, d
+
+
+def build_correspondence(source_desc, target_desc):
+    """geometric_registration/common.py:5-21 restated (NumPy, fp32 in -> fp32 distances): mutual argmin of
+    sqrt(2 - 2 S T^T); np.argmin picks the first NaN of a row/column if there is one."""
+    import numpy as np
+    s = np.asarray(source_desc)
+    t = np.asarray(target_desc)
+    with np.errstate(invalid="ignore"):
+        distance = np.sqrt(2 - 2 * (s @ t.T))
+    source_idx = np.argmin(distance, axis=1)
+    target_idx = np.argmin(distance, axis=0)
+    result = [[i, source_idx[i]] for i in range(len(source_idx)) if target_idx[source_idx[i]] == i]
+    return np.array(result)

@@ -148,3 +148,22 @@ def kpfcnn_state_dict(config, seed=0):
             sd[k] = torch.from_numpy(rng.uniform(-0.05, 0.05, size=shapes[k]).astype(np.float32))
     fill_kernel_points(sd, kp_radius, config.num_kernel_points, seed)
     return sd
+
+
+# ------------------------------------------------------------------------------------------- descriptor matching (f3)
+MATCHING_CASES = {"m_700_650": (700, 650, 11), "m_250_250": (250, 250, 12), "m_1_40": (1, 40, 13), "m_2000_1800": (2000, 1800, 14)}
+
+
+def matching_case(ns, nt, seed, dim=32, overlap=0.6, noise=0.15):
+    """Two sets of unit descriptors sharing `overlap` of their points up to noise (so mutual matches exist)."""
+    rng = np.random.default_rng(seed)
+    base = rng.standard_normal((max(ns, nt), dim))
+    s = base[:ns] + 0.0 * rng.standard_normal((ns, dim))
+    t = base[:nt].copy()
+    fresh = rng.random(nt) > overlap
+    t[fresh] = rng.standard_normal((int(fresh.sum()), dim))
+    t += noise * rng.standard_normal((nt, dim))
+    t = t[rng.permutation(nt)]
+    s /= np.linalg.norm(s, axis=1, keepdims=True)
+    t /= np.linalg.norm(t, axis=1, keepdims=True)
+    return s.astype(np.float32), t.astype(np.float32)
