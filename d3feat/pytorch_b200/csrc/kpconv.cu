@@ -1,19 +1,19 @@
-// KPConv forward / backward (replaces the ATen chain of models/blocks.py:237-382).
+// KPConv forward / backward (replaces the ATen chain of models/blocks.py:237-382): C ABI, workspace layout, the wiring
+// of gather kernel -> contraction GEMM, and the first-generation (v1) gather kernels kept as a selectable baseline.
 //
 // Math per query i:
 //   w[i,k,h]  = influence(|| (s[idx[i,h]] - q[i]) - kp[k] ||^2)           (shadow idx -> no contribution)
 //   wf[i,k,:] = m[i,k] * sum_h w[i,k,h] * x[idx[i,h], :]
-//   out[i,:]  = (sum_k wf[i,k,:] @ W[k]) / max(1, #{h : sum_c x[idx[i,h],c] > 0})
+//   out[i,:]  = act((sum_k wf[i,k,:] @ W[k]) / max(1, #{h : sum_c x[idx[i,h],c] > 0}) + bias)
 //
 // Kernels
 //   kp_rowpos     : per support row, (sum_c x[j,c] > 0)                      (density count, blocks.py:377)
-//   kp_correlate  : one warp per query.  Phase 1: lanes over neighbours compute the K influences into
-//                   shared memory (+ in-range filter / min_d2 for deformed kernels).  Phase 2: lanes over
-//                   channels gather each neighbour row once (coalesced) and accumulate all K products
-//                   in registers; wf is written [Nq, K*Cin] row-major = the A operand of the contraction.
-//   kp_gemm       : fp32 tiled GEMM (NN / NT / TN, optional split-K) used for
-//                   out = diag(inv_n) wf W,  dwf = diag(inv_n) g W^T,  dW = wf^T diag(inv_n) g
-//   kp_scatter    : one warp per query: dx[idx] += sum_k w dwf  (+ kernel-point / modulation grads)
+//   gather        : kp2_correlate (kpconv2.cu, default) or v1 kp_correlate (this file): wf [Nq, K*Cin] row-major = the A
+//                   operand of the contraction
+//   contraction   : d3f_gemm_launch (gemm.cu / gemm_tcgen05.cu), 3xTF32 on tcgen05 with fused epilogue:
+//                   out = act(diag(inv_n) wf W + bias),  dW = wf^T diag(inv_n) g,  dwf = diag(inv_n) g W^T
+//   backward data : kp2t_correlate over transposed neighbour lists + GEMM with W^T (atomic-free), or dwf GEMM +
+//                   kp2_scatter / v1 kp_scatter (reductions)
 #include "common.cuh"
 #include "gemm.cuh"
 #include "kpconv.cuh"
@@ -201,107 +201,6 @@ kp_correlate_kernel(KpArgs a, float* __restrict__ wf, float* __restrict__ wf_unm
             }
         }
     }
-}
-
-// --------------------------------------------------------------------------------------------
-// fp32 tiled GEMM.  C[M,N] (+)= rs[m] * sum_k opA(m,k) * ks[k] * opB(k,n)
-//   TA=false: opA(m,k)=A[m*lda+k]   TA=true: opA(m,k)=A[k*lda+m]
-//   TB=false: opB(k,n)=B[k*ldb+n]   TB=true: opB(k,n)=B[n*ldb+k]
-// gridDim.z > 1: split-K, partial tiles are atomically added into a pre-zeroed C.
-constexpr int GM = 64, GN = 64, GK = 16;
-
-template <bool TA, bool TB>
-__global__ void __launch_bounds__(256)
-kp_gemm_kernel(int M, int N, int Kd, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
-               float* __restrict__ C, int ldc, const float* __restrict__ rs, const float* __restrict__ ks,
-               int k_per_split) {
-    __shared__ float As[GK][GM + 4];
-    __shared__ float Bs[GK][GN + 4];
-    const int tid = threadIdx.x;
-    const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
-    const int kbeg = blockIdx.z * k_per_split, kend = min(Kd, kbeg + k_per_split);
-    const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, 4x4 outputs each
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
-    for (int k0 = kbeg; k0 < kend; k0 += GK) {
-        // A tile: GM x GK
-#pragma unroll
-        for (int r = 0; r < (GM * GK) / 256; ++r) {
-            const int e = tid + r * 256;
-            int m, k;
-            if (TA) { m = e % GM; k = e / GM; } else { k = e % GK; m = e / GK; }
-            const int gm = m0 + m, gk = k0 + k;
-            float v = 0.f;
-            if (gm < M && gk < kend) v = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
-            As[k][m] = v;
-        }
-#pragma unroll
-        for (int r = 0; r < (GN * GK) / 256; ++r) {
-            const int e = tid + r * 256;
-            int n, k;
-            if (TB) { k = e % GK; n = e / GK; } else { n = e % GN; k = e / GN; }
-            const int gn = n0 + n, gk = k0 + k;
-            float v = 0.f;
-            if (gn < N && gk < kend) {
-                v = TB ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
-                if (ks) v *= ks[gk];
-            }
-            Bs[k][n] = v;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < GK; ++k) {
-            const float4 av = *(const float4*)&As[k][ty * 4];
-            const float4 bv = *(const float4*)&Bs[k][tx * 4];
-            const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int gm = m0 + ty * 4 + i;
-        if (gm >= M) continue;
-        const float sc = rs ? rs[gm] : 1.0f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int gn = n0 + tx * 4 + j;
-            if (gn >= N) continue;
-            const float v = acc[i][j] * sc;
-            if (gridDim.z > 1) atomicAdd(&C[(size_t)gm * ldc + gn], v);
-            else C[(size_t)gm * ldc + gn] = v;
-        }
-    }
-}
-
-template <bool TA, bool TB>
-int kp_gemm(int M, int N, int Kd, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
-            const float* rs, const float* ks, cudaStream_t stream) {
-    if (M <= 0 || N <= 0) return D3F_OK;
-    const int tiles = d3f_ceil_div(M, GM) * d3f_ceil_div(N, GN);
-    int splits = 1;
-    if (Kd > 0) {
-        // aim for >= 2 waves of 148 SMs x 2 CTAs when the output grid alone cannot fill the chip
-        const int target = 592;
-        if (tiles < target) splits = min(d3f_ceil_div(target, tiles), d3f_ceil_div(Kd, 4 * GK));
-        if (splits < 1) splits = 1;
-    }
-    int kps = d3f_ceil_div(d3f_ceil_div(Kd > 0 ? Kd : 1, splits), GK) * GK;
-    splits = d3f_ceil_div(Kd > 0 ? Kd : 1, kps);
-    if (splits > 1 || Kd == 0)
-        D3F_CHECK_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * ldc, stream));
-    if (Kd == 0) return D3F_OK;
-    dim3 grid(d3f_ceil_div(N, GN), d3f_ceil_div(M, GM), splits);
-    kp_gemm_kernel<TA, TB><<<grid, 256, 0, stream>>>(M, N, Kd, A, lda, B, ldb, C, ldc, rs, ks, kps);
-    D3F_CHECK_LAUNCH();
-    return D3F_OK;
 }
 
 // --------------------------------------------------------------------------------------------
