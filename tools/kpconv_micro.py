@@ -42,7 +42,8 @@ for name, lvl, kind, cin, cout in cases:
     t_tr = timed(lambda: ops.neighbors_transpose(inds, s.shape[0]))
     print("%-22s neighbors_transpose: %.1f us" % (name, t_tr))
     for impl, label, env in ((0, "v1", None), (1, "v2-ffma", None), (2, "v2-mma", None), (2, "v2-mma/scalar-red", "scalar"),
-                             (2, "v2-mma/transposed", "t")):
+                             (2, "v2-mma/transposed", "t"), (2, "v2-mma/transp+skinny", "sk")):
+        lib.d3f_set_gemm_skinny(1 if env == "sk" else 0)
         lib.d3f_set_kpconv_impl(impl)
         if hasattr(lib, "d3f_set_scatter_vec"):
             lib.d3f_set_scatter_vec(0 if env == "scalar" else 2)
@@ -62,9 +63,10 @@ for name, lvl, kind, cin, cout in cases:
         t_g = ev[0].elapsed_time(ev[1]) * 1e3
         _, wf, wf_un, inv_n, _ = out
         t_b = timed(lambda: ops.kpconv_backward(q, s, inds, x, W, kpl, ext, "linear", "sum", False, None, wf, wf_un, inv_n, g,
-                                                cin > 1, True, False, False, transpose=tr if env == "t" else None))
+                                                cin > 1, True, False, False, transpose=tr if env in ("t", "sk") else None))
         print("%-22s %-18s %10.1f %10.1f %10.1f" % (name, label, t_g, t_f, t_b))
 lib.d3f_set_kpconv_impl(-1)
+lib.d3f_set_gemm_skinny(-1)
 
 print("\nGEMM pipelines (us per call, back to back):")
 shapes = [(40000, 32, 480, False, False), (13312, 32, 480, False, False), (13312, 64, 960, False, False), (40000, 480, 32, False, True),
@@ -79,8 +81,11 @@ for (M, N, K, ta, tb) in shapes:
         for det in (False, True):
             row.append(timed(lambda: ops.gemm(a, b, ta, tb, deterministic=det)))
     lib.d3f_set_gemm_pipeline(-1)
+    lib.d3f_set_gemm_skinny(1)
+    row.append(timed(lambda: ops.gemm(a, b, ta, tb, deterministic=True)))
+    lib.d3f_set_gemm_skinny(-1)
     fl = 2.0 * M * N * K
-    print("M=%6d N=%5d K=%6d ta=%d tb=%d | reg: %6.1f (det %6.1f) | cp.async: %6.1f (det %6.1f) | warp-spec: %6.1f (det %6.1f) | %.1f TFLOP/s best"
-          % (M, N, K, ta, tb, row[0], row[1], row[2], row[3], row[4], row[5], fl / min(row) / 1e6))
+    print("M=%6d N=%5d K=%6d ta=%d tb=%d | reg: %6.1f (det %6.1f) | cp.async: %6.1f (det %6.1f) | warp-spec: %6.1f (det %6.1f) | skinny(if eligible): %6.1f | %.1f TFLOP/s best"
+          % (M, N, K, ta, tb, row[0], row[1], row[2], row[3], row[4], row[5], row[6], fl / min(row) / 1e6))
 if lib.d3f_gemm_tcgen05_failed() != 0:
     print("WARNING: a tcgen05 GEMM gave up waiting on an mbarrier")
