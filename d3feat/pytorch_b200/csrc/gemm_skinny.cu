@@ -30,7 +30,7 @@ __device__ __forceinline__ void sk_mma(float (&c)[4], const uint32_t (&a)[4], ui
 
 // NT8 = N tile / 8 (4 or 8); KC = K chunk resident in shared memory (multiple of 16)
 template <int NT8, bool TB>
-__global__ void __launch_bounds__(768)
+__global__ void __launch_bounds__(576)
 sk_gemm_kernel(D3fGemm g, int KC, int n_tiles, int total_warps) {
     extern __shared__ float4 bs[];        // [KC/16][2][NT8][32] float4 {b0_hi, b1_hi, b0_lo, b1_lo}
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -80,34 +80,48 @@ sk_gemm_kernel(D3fGemm g, int KC, int n_tiles, int total_warps) {
             }
             if (!resident) __syncthreads();
             if (active) {
+                // A: a ring of PF groups (16 k each) per row pair is always in flight -- with one group the kernel kept
+                // ~2.5 MB in flight chip-wide and ran at 1.9 TB/s (profiles/r1m_micro_kpconv_gemm.txt)
                 const int ngroups = kc >> 4;
-                float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
-                if (okA) va = __ldg((const float4*)(pa + k0));
-                if (okB) vb = __ldg((const float4*)(pb + k0));
-                for (int s = 0; s < ngroups; ++s) {
-                    float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;     // prefetch the next group of 16 k
-                    if (s + 1 < ngroups) {
-                        if (okA) na = __ldg((const float4*)(pa + k0 + 16 * (s + 1)));
-                        if (okB) nb = __ldg((const float4*)(pb + k0 + 16 * (s + 1)));
+                constexpr int PF = 4;
+                float4 ra[PF], rb[PF];
+#pragma unroll
+                for (int j = 0; j < PF; ++j) {
+                    ra[j] = rb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (j < ngroups) {
+                        if (okA) ra[j] = __ldg((const float4*)(pa + k0 + 16 * j));
+                        if (okB) rb[j] = __ldg((const float4*)(pb + k0 + 16 * j));
                     }
-                    const float xa[4] = {va.x, va.y, va.z, va.w}, xb[4] = {vb.x, vb.y, vb.z, vb.w};
+                }
+                for (int s0 = 0; s0 < ngroups; s0 += PF) {
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        uint32_t ah[4], al[4];
-                        sk_split(xa[2 * u], ah[0], al[0]);          // a0: row gq,   position tq
-                        sk_split(xb[2 * u], ah[1], al[1]);          // a1: row gq+8, position tq
-                        sk_split(xa[2 * u + 1], ah[2], al[2]);      // a2: row gq,   position tq+4
-                        sk_split(xb[2 * u + 1], ah[3], al[3]);      // a3: row gq+8, position tq+4
-                        const float4* bp = bs + ((size_t)(s * 2 + u) * NT8) * 32 + lane;
+                    for (int j = 0; j < PF; ++j) {
+                        const int s = s0 + j;
+                        if (s < ngroups) {
+                            const float4 va = ra[j], vb = rb[j];
+                            if (s + PF < ngroups) {
+                                if (okA) ra[j] = __ldg((const float4*)(pa + k0 + 16 * (s + PF)));
+                                if (okB) rb[j] = __ldg((const float4*)(pb + k0 + 16 * (s + PF)));
+                            }
+                            const float xa[4] = {va.x, va.y, va.z, va.w}, xb[4] = {vb.x, vb.y, vb.z, vb.w};
 #pragma unroll
-                        for (int nt = 0; nt < NT8; ++nt) {
-                            const float4 b = bp[nt * 32];
-                            sk_mma(acc[nt], al, __float_as_uint(b.x), __float_as_uint(b.y));
-                            sk_mma(acc[nt], ah, __float_as_uint(b.z), __float_as_uint(b.w));
-                            sk_mma(acc[nt], ah, __float_as_uint(b.x), __float_as_uint(b.y));
+                            for (int u = 0; u < 2; ++u) {
+                                uint32_t ah[4], al[4];
+                                sk_split(xa[2 * u], ah[0], al[0]);          // a0: row gq,   position tq
+                                sk_split(xb[2 * u], ah[1], al[1]);          // a1: row gq+8, position tq
+                                sk_split(xa[2 * u + 1], ah[2], al[2]);      // a2: row gq,   position tq+4
+                                sk_split(xb[2 * u + 1], ah[3], al[3]);      // a3: row gq+8, position tq+4
+                                const float4* bp = bs + ((size_t)(s * 2 + u) * NT8) * 32 + lane;
+#pragma unroll
+                                for (int nt = 0; nt < NT8; ++nt) {
+                                    const float4 b = bp[nt * 32];
+                                    sk_mma(acc[nt], al, __float_as_uint(b.x), __float_as_uint(b.y));
+                                    sk_mma(acc[nt], ah, __float_as_uint(b.z), __float_as_uint(b.w));
+                                    sk_mma(acc[nt], ah, __float_as_uint(b.x), __float_as_uint(b.y));
+                                }
+                            }
                         }
                     }
-                    va = na; vb = nb;
                 }
             }
         }
@@ -140,19 +154,21 @@ int g_skinny = -1;
 int skinny_enabled() {
     if (g_skinny < 0) {
         const char* e = getenv("D3F_GEMM_SKINNY");
-        g_skinny = e ? (e[0] != '0') : D3F_GEMM_SKINNY_DEFAULT;
+        g_skinny = e ? (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1)) : D3F_GEMM_SKINNY_DEFAULT;
     }
     return g_skinny;
 }
 
 }  // namespace
 
-extern "C" void d3f_set_gemm_skinny(int on) { g_skinny = on < 0 ? -1 : (on ? 1 : 0); }
+extern "C" void d3f_set_gemm_skinny(int on) { g_skinny = on < 0 ? -1 : (on > 2 ? 2 : on); }
 
 // true if the problem is one this kernel takes (the caller has already ruled out split-K)
 bool d3f_gemm_skinny_eligible(const D3fGemm& g, bool ta, bool tb) {
-    if (!skinny_enabled() || ta || g.ks || g.partial) return false;
+    const int mode = skinny_enabled();      // 1 = only where it was measured to win, 2 = every problem the kernel takes
+    if (!mode || ta || g.ks || g.partial) return false;
     if (g.N < 1 || g.N > 64 || g.M < 2048 || g.K < 16 || (g.K & 15)) return false;
+    if (mode == 1 && !(g.M >= 16384 && g.K <= (g.N <= 32 ? 480 : 240))) return false;   // one resident B chunk, >= 7 warps/SM
     if ((g.lda & 3) || (((size_t)g.A) & 15)) return false;
     if (g.bblk && (!tb || (g.bblk & 15))) return false;
     return true;
@@ -165,10 +181,10 @@ int d3f_gemm_skinny_launch(const D3fGemm& g, bool tb, cudaStream_t stream) {
     const size_t smem = (size_t)kc * nt8 * 8 * 8;            // kc * N8 * 2 floats... = kc/16 * 2 * nt8 * 32 * 16 bytes
     const int n_tiles = d3f_ceil_div(g.M, 16);
     // whole waves over 148 SMs: the fewest rounds r whose warp count per CTA fits, then the warps that cover the tiles
-    int warps = 24, rounds = 1;
+    int warps = 18, rounds = 1;
     for (rounds = 1; ; ++rounds) {
         warps = d3f_ceil_div(n_tiles, 148 * rounds);
-        if (warps <= 24) break;
+        if (warps <= 18) break;
     }
     if (warps < 4) warps = 4;
     const int ctas = d3f_ceil_div(n_tiles, warps * rounds) < 148 ? d3f_ceil_div(n_tiles, warps * rounds) : 148;

@@ -281,8 +281,9 @@ void d3f_set_gemm_impl(int use_tcgen05);
  * cp.async ring (needs a 16-byte aligned A); 2 = warp-specialised (8 converter warps + 1 MMA warp, two operand stages);
  * -1 = default (environment D3F_GEMM_PIPELINE = reg | cpasync | ws, else the library's built-in choice). */
 void d3f_set_gemm_pipeline(int variant);
-/* 1 = route large-M (>= 2048), N <= 64, K % 16 == 0, non-transposed-A problems to the B-resident mma.sync kernel
- * (csrc/gemm_skinny.cu), 0 = never, -1 = default (environment D3F_GEMM_SKINNY, else the library's built-in choice). */
+/* B-resident mma.sync kernel (csrc/gemm_skinny.cu) for N <= 64, K % 16 == 0, non-transposed-A problems: 2 = every such
+ * problem with M >= 2048, 1 = only large-M problems whose B fits one resident chunk, 0 = never,
+ * -1 = default (environment D3F_GEMM_SKINNY = 0 | 1 | 2, else the library's built-in choice). */
 void d3f_set_gemm_skinny(int on);
 int d3f_gemm_tcgen05_failed(void);
 int d3f_gemm(int trans_a, int trans_b, int M, int N, int K, const float* A, int lda, const float* B, int ldb,

@@ -43,7 +43,7 @@ for name, lvl, kind, cin, cout in cases:
     print("%-22s neighbors_transpose: %.1f us" % (name, t_tr))
     for impl, label, env in ((0, "v1", None), (1, "v2-ffma", None), (2, "v2-mma", None), (2, "v2-mma/scalar-red", "scalar"),
                              (2, "v2-mma/transposed", "t"), (2, "v2-mma/transp+skinny", "sk")):
-        lib.d3f_set_gemm_skinny(1 if env == "sk" else 0)
+        lib.d3f_set_gemm_skinny(2 if env == "sk" else 0)
         lib.d3f_set_kpconv_impl(impl)
         if hasattr(lib, "d3f_set_scatter_vec"):
             lib.d3f_set_scatter_vec(0 if env == "scalar" else 2)
@@ -81,7 +81,7 @@ for (M, N, K, ta, tb) in shapes:
         for det in (False, True):
             row.append(timed(lambda: ops.gemm(a, b, ta, tb, deterministic=det)))
     lib.d3f_set_gemm_pipeline(-1)
-    lib.d3f_set_gemm_skinny(1)
+    lib.d3f_set_gemm_skinny(2)
     row.append(timed(lambda: ops.gemm(a, b, ta, tb, deterministic=True)))
     lib.d3f_set_gemm_skinny(-1)
     fl = 2.0 * M * N * K
