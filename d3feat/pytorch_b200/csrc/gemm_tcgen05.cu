@@ -90,6 +90,15 @@ __device__ __forceinline__ void st_split(char* hi, char* lo, uint32_t off, float
 
 __device__ int g_tc5_fail = 0;
 
+// -DD3F_TC5_TIMING (tools/tc5_timing.py builds a separate diagnostic library): per-phase clock64() sums of the main
+// loop for threads 0 (MMA issuer) and 255 of one CTA in the middle of the grid.  Never compiled into the product.
+#ifdef D3F_TC5_TIMING
+__device__ unsigned long long g_tc5_t[32];
+#define TC5_T(i) do { if (timed) { const long long now_ = clock64(); tacc[i] += now_ - tlast; tlast = now_; } } while (0)
+#else
+#define TC5_T(i) do { } while (0)
+#endif
+
 template <bool TA, bool TB, int BN>
 __global__ void __launch_bounds__(NT, BN >= 128 ? 3 : 4)
 tc5_gemm_kernel(D3fGemm g) {
@@ -194,14 +203,25 @@ tc5_gemm_kernel(D3fGemm g) {
         }
     };
 
+#ifdef D3F_TC5_TIMING
+    const bool timed = (tid == 0 || tid == 255) && blockIdx.x == 0 && blockIdx.y == gridDim.y / 2 && blockIdx.z == 0;
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+    const long long tstart = tlast;
+#endif
     if (nk > 0) load_tile(kbeg);
+    TC5_T(6);                                                                      // prologue: alloc, barrier init, first loads issued
     for (int kt = 0; kt < nk; ++kt) {
         if (kt >= 1) mbar_wait(smem_u32(&bars[0]), (kt - 1) & 1, &g_tc5_fail);   // MMAs of tile kt-1 have read the stage
+        TC5_T(0);
         store_tile();
+        TC5_T(1);
         if (kt + 1 < nk) load_tile(kbeg + (kt + 1) * BK);                          // global loads overlap the MMAs
+        TC5_T(2);
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");              // generic-proxy stores -> async proxy (UMMA)
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        TC5_T(3);
         __syncthreads();
+        TC5_T(4);
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const uint32_t a_hi = smem_u32(smem), a_lo = a_hi + A_TILE;
@@ -220,11 +240,13 @@ tc5_gemm_kernel(D3fGemm g) {
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
                          :: "r"(smem_u32(&bars[0])) : "memory");
         }
+        TC5_T(5);
     }
 
     // ---- epilogue
     if (nk > 0) mbar_wait(smem_u32(&bars[0]), (nk - 1) & 1, &g_tc5_fail);
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    TC5_T(0);
     // TMEM -> registers (one row per thread) -> shared C tile [128][BN+4] (row stride = 4 banks mod 32: the
     // 128-bit stores of a quarter warp are conflict-free) -> 128-bit row-contiguous global stores.
     constexpr int LDC_S = BN + 4;
@@ -289,6 +311,15 @@ tc5_gemm_kernel(D3fGemm g) {
             else for (int e = 0; e < 4; ++e) if (n + e < g.N) dst[e] = xs[e];
         }
     }
+    TC5_T(7);                                                                      // epilogue
+#ifdef D3F_TC5_TIMING
+    if (timed) {
+        unsigned long long* o = g_tc5_t + (tid == 0 ? 0 : 16);
+        for (int i = 0; i < 8; ++i) o[i] = (unsigned long long)tacc[i];
+        o[8] = (unsigned long long)(clock64() - tstart);
+        o[9] = (unsigned long long)nk;
+    }
+#endif
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     if (warp == 0)
@@ -858,6 +889,12 @@ int d3f_gemm_tcgen05_launch(const D3fGemm& g, bool ta, bool tb, int splits, cuda
     d3f_set_error("gemm: TT mode is not used on the hot path");
     return D3F_ERR_UNSUPPORTED;
 }
+
+#ifdef D3F_TC5_TIMING
+extern "C" int d3f_tc5_timing(unsigned long long* out32) {
+    return cudaMemcpyFromSymbol(out32, g_tc5_t, sizeof(unsigned long long) * 32) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 // 1 if any tcgen05 GEMM gave up waiting on an mbarrier (diagnostic; reads a device symbol -> synchronises)
 extern "C" int d3f_gemm_tcgen05_failed(void) {
