@@ -819,17 +819,297 @@ tc7_gemm_kernel(D3fGemm g) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_d), "r"(TMEM_COLS) : "memory");
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// tc8 (EXPERIMENTAL -- written at the end of round 1 from the clock64 breakdown in profiles/r1p_tc5_phase_timing.txt,
+// not yet run on a GPU; selectable with D3F_GEMM_PIPELINE=tmem only): the A operand lives in TENSOR MEMORY.
+//
+// tc5/tc6/tc7 all push A through shared memory twice over (hi + lo stores, then every MMA re-reads the 128-row tile:
+// ~5x the tile's bytes through a 128 B/clk pipe, ~3700 cycles per K tile).  Here
+//   * warps 0-3 own 32 rows each: coalesced 128-bit loads of the [32 x 32] fp32 slab (one K tile ahead, in registers),
+//     a swizzled 4 KB shared-memory transpose so that a thread holds ITS row, hi = the raw fp32 bits (the tensor core
+//     drops the low 13 bits), lo = v - trunc(v), and two tcgen05.st.32x32b.x32 into the stage's TMEM columns;
+//     with A stored [K][M] (TA) a thread's row is already what coalesced loads give: no transpose;
+//   * warps 4-7 split the small B tile into the usual K-major shared-memory stage;
+//   * warp 8 issues tcgen05.mma with A from TMEM ([taddr]) and B from a shared-memory descriptor, two stages, the
+//     same full[s] / empty[s] mbarrier protocol as tc7.
+// TMEM columns (256 allocated, 2 CTAs/SM): accumulator [0, BN) | stage s: A_hi [128 + 64s, +32), A_lo [160 + 64s, +32).
+constexpr int NT8 = 288;
+template <int BN> struct Cfg8 {
+    static constexpr int B_STAGE = 2 * Cfg<BN>::B_TILE;                 // B_hi | B_lo
+    static constexpr int SLAB = 32 * 32 * 4;                            // one warp's transpose slab
+    static constexpr int C_BYTES = BM * (BN + 4) * 4;
+    static constexpr int WORK = 2 * B_STAGE + 4 * SLAB;
+    static constexpr int SMEM_BYTES = (WORK > C_BYTES ? WORK : C_BYTES) + 128;
+};
+
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};\n"
+        :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+           "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+           "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+           "r"(v[30]), "r"(v[31]) : "memory");
+}
+
+template <bool TA, bool TB, int BN>
+__global__ void __launch_bounds__(NT8, 2)
+tc8_gemm_kernel(D3fGemm g) {
+    constexpr int B_LBO = Cfg<BN>::B_LBO, B_TILE = Cfg<BN>::B_TILE, B_STAGE = Cfg8<BN>::B_STAGE, SLAB = Cfg8<BN>::SLAB;
+    constexpr uint32_t TMEM_COLS = 256, A_COL0 = 128;
+    extern __shared__ __align__(128) char smem[];
+    char* slabs = smem + 2 * B_STAGE;
+    uint64_t* bars = (uint64_t*)(smem + Cfg8<BN>::SMEM_BYTES - 128);     // full[0], full[1], empty[0], empty[1]
+    uint32_t* tmem_ptr = (uint32_t*)(smem + Cfg8<BN>::SMEM_BYTES - 64);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kbeg = blockIdx.z * g.k_per_split, kend = min(g.K, kbeg + g.k_per_split);
+    const int nk = (kend - kbeg + BK - 1) / BK;
+    const bool a_vec = (g.lda & 3) == 0 && (((size_t)g.A) & 15) == 0;
+    const bool b_vec = (g.ldb & 3) == 0 && (((size_t)g.B) & 15) == 0;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(tmem_ptr)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    if (tid == 32) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(&bars[0])), "r"(8) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(&bars[1])), "r"(8) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(&bars[2])), "r"(1) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(&bars[3])), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem_d = *tmem_ptr;
+
+    if (warp == 8) {
+        // ---------------- MMA issuer (whole warp walks the tiles, lane 0 issues)
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        for (int kt = 0; kt < nk; ++kt) {
+            const int s = kt & 1;
+            mbar_wait(smem_u32(&bars[s]), (kt >> 1) & 1, &g_tc5_fail, 1LL << 18);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            if (lane == 0) {
+                const uint32_t b_hi = smem_u32(smem) + s * B_STAGE, b_lo = b_hi + B_TILE;
+                const uint32_t a_hi = tmem_d + A_COL0 + 64 * s, a_lo = a_hi + 32;
+#pragma unroll
+                for (int ks = 0; ks < BK / 8; ++ks) {
+                    const uint32_t bo = ks * 2 * B_LBO;
+                    const uint64_t dbh = make_desc(b_hi + bo, B_LBO, SBO), dbl = make_desc(b_lo + bo, B_LBO, SBO);
+                    mma_tf32_ts(tmem_d, a_lo + 8 * ks, dbh, idesc, (kt | ks) ? 1u : 0u);
+                    mma_tf32_ts(tmem_d, a_hi + 8 * ks, dbl, idesc, 1u);
+                    mma_tf32_ts(tmem_d, a_hi + 8 * ks, dbh, idesc, 1u);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+                             :: "r"(smem_u32(&bars[2 + s])) : "memory");
+            }
+            __syncwarp();
+        }
+    } else if (warp < 4) {
+        // ---------------- A converters: rows 32*warp .. +31 of the tile -> TMEM
+        char* slab = slabs + warp * SLAB;
+        const int rbase = 32 * warp;
+        float4 pre[8];                       // !TA: slab of the next tile as coalesced float4 (row 4j + lane/8, k4 = lane%8)
+        float prt[TA ? 32 : 1];              //  TA: this thread's row of the next tile (k = 0..31), coalesced over lanes
+        auto load_a = [&](int kt) {
+            const int k0 = kbeg + kt * BK;
+            if (!TA) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int m = m0 + rbase + 4 * j + (lane >> 3), k = k0 + (lane & 7) * 4;
+                    pre[j] = (m < g.M) ? ld4g(g.A + (size_t)m * g.lda + k, kend - k, a_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else {
+                const int m = m0 + rbase + lane;
+#pragma unroll
+                for (int k = 0; k < 32; ++k)
+                    prt[TA ? k : 0] = (m < g.M && k0 + k < kend) ? __ldg(g.A + (size_t)(k0 + k) * g.lda + m) : 0.f;
+            }
+        };
+        if (nk > 0) load_a(0);
+        for (int kt = 0; kt < nk; ++kt) {
+            const int s = kt & 1;
+            float row[32];
+            if (!TA) {
+                __syncwarp();                                   // the previous tile's row reads of the slab are done
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int r = 4 * j + (lane >> 3), q = lane & 7;
+                    *(float4*)(slab + (r * 8 + (q ^ (r & 7))) * 16) = pre[j];
+                }
+                __syncwarp();
+                if (kt + 1 < nk) load_a(kt + 1);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {                   // my row = lane; chunk q sits at position q ^ (lane & 7)
+                    const float4 v = *(const float4*)(slab + (lane * 8 + (q ^ (lane & 7))) * 16);
+                    row[4 * q] = v.x; row[4 * q + 1] = v.y; row[4 * q + 2] = v.z; row[4 * q + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) row[k] = prt[TA ? k : 0];
+                if (kt + 1 < nk) load_a(kt + 1);
+            }
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                hi[k] = __float_as_uint(row[k]);                                        // tensor core drops the low 13 bits
+                lo[k] = __float_as_uint(row[k] - __uint_as_float(hi[k] & 0xffffe000u)); // exact remainder
+            }
+            if (kt >= 2) mbar_wait(smem_u32(&bars[2 + s]), ((kt >> 1) - 1) & 1, &g_tc5_fail, 1LL << 18);   // stage s free
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const uint32_t ta = tmem_d + ((uint32_t)rbase << 16) + A_COL0 + 64 * s;
+            tmem_st32(ta, hi);
+            tmem_st32(ta + 32, lo);
+            asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars[s]));
+        }
+        if (nk > 0) mbar_wait(smem_u32(&bars[2 + ((nk - 1) & 1)]), ((nk - 1) >> 1) & 1, &g_tc5_fail, 1LL << 18);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    } else {
+        // ---------------- B converters (128 threads): global -> registers (one tile ahead) -> hi / lo shared-memory stage
+        const int u = tid - 128;
+        float4 rb[4];
+        auto load_b = [&](int kt) {
+            const int k0 = kbeg + kt * BK;
+            if (TB) {       // B[n][k]: BN rows x 8 float4 = BN/16 per thread
+#pragma unroll
+                for (int r = 0; r < BN / 16; ++r) {
+                    const int n = n0 + (u >> 3) + 16 * r, k = k0 + (u & 7) * 4;
+                    const size_t kb = g.bblk ? (size_t)(k / g.bblk) * g.bblk_stride + (k % g.bblk) : (size_t)k;
+                    rb[r] = (n < g.N) ? ld4g(g.B + (size_t)n * g.ldb + kb, kend - k, b_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else if (u < 2 * BN) {   // B[k][n]: thread = (4 k rows, 4 consecutive n)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = k0 + (u / (BN / 4)) * 4 + j, n = n0 + (u % (BN / 4)) * 4;
+                    float4 v = (k < kend) ? ld4g(g.B + (size_t)k * g.ldb + n, g.N - n, b_vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (g.ks && k < kend) { const float sc = g.ks[k]; v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc; }
+                    rb[j] = v;
+                }
+            }
+        };
+        if (nk > 0) load_b(0);
+        for (int kt = 0; kt < nk; ++kt) {
+            const int s = kt & 1;
+            if (kt >= 2) mbar_wait(smem_u32(&bars[2 + s]), ((kt >> 1) - 1) & 1, &g_tc5_fail, 1LL << 18);
+            char* b_hi = smem + s * B_STAGE;
+            char* b_lo = b_hi + B_TILE;
+            if (TB) {
+#pragma unroll
+                for (int r = 0; r < BN / 16; ++r) {
+                    const int n = (u >> 3) + 16 * r, k4 = u & 7;
+                    st_split(b_hi, b_lo, k4 * B_LBO + (n >> 3) * SBO + (n & 7) * 16, rb[r]);
+                }
+            } else if (u < 2 * BN) {
+                const int k4 = u / (BN / 4), nb = (u % (BN / 4)) * 4;
+                const float t[4][4] = {{rb[0].x, rb[1].x, rb[2].x, rb[3].x}, {rb[0].y, rb[1].y, rb[2].y, rb[3].y},
+                                       {rb[0].z, rb[1].z, rb[2].z, rb[3].z}, {rb[0].w, rb[1].w, rb[2].w, rb[3].w}};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int n = nb + e;
+                    st_split(b_hi, b_lo, k4 * B_LBO + (n >> 3) * SBO + (n & 7) * 16, make_float4(t[e][0], t[e][1], t[e][2], t[e][3]));
+                }
+            }
+            if (kt + 1 < nk) load_b(kt + 1);
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars[s]));
+        }
+        if (nk > 0) mbar_wait(smem_u32(&bars[2 + ((nk - 1) & 1)]), ((nk - 1) >> 1) & 1, &g_tc5_fail, 1LL << 18);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    }
+
+    // ---- epilogue (tc5's): TMEM -> registers -> shared C tile [128][BN+4] -> coalesced global stores
+    __syncthreads();                     // every warp is past its last shared-memory / TMEM use of the main loop
+    constexpr int LDC_S = BN + 4;
+    float* cs = (float*)smem;
+    if (warp < 8) {
+        const int r_loc = (warp & 3) * 32 + lane, col0 = (warp >> 2) * (BN / 2);
+#pragma unroll
+        for (int part = 0; part < BN / 32; ++part) {
+            uint32_t v[16];
+            const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(col0 + part * 16);
+            if (nk > 0) {
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                             : "r"(taddr) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] = 0u;
+            }
+#pragma unroll
+            for (int e = 0; e < 16; e += 4)
+                *(uint4*)&cs[r_loc * LDC_S + col0 + part * 16 + e] = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+        }
+    }
+    __syncthreads();
+    if (warp < 8) {
+        const bool atomic = gridDim.z > 1 && !g.partial;
+        constexpr int TPR = BN / 4, RPP = 256 / TPR;
+        const int c4 = (tid % TPR) * 4, n = n0 + c4;
+        const bool vec_ok = g.partial ? ((g.N & 3) == 0) : ((g.ldc & 3) == 0 && (((size_t)g.C) & 15) == 0);
+#pragma unroll
+        for (int it = 0; it < BM / RPP; ++it) {
+            const int r_loc = tid / TPR + RPP * it, row = m0 + r_loc;
+            if (row >= g.M || n >= g.N) continue;
+            float4 x = *(const float4*)&cs[r_loc * LDC_S + c4];
+            float xs[4] = {x.x, x.y, x.z, x.w};
+            if (g.partial) {
+                float* dst = g.partial + (size_t)blockIdx.z * g.M * g.N + (size_t)row * g.N + n;
+                if (vec_ok && n + 3 < g.N) *(float4*)dst = x;
+                else for (int e = 0; e < 4; ++e) if (n + e < g.N) dst[e] = xs[e];
+                continue;
+            }
+            const float sc = g.rs ? g.rs[row] : 1.0f;
+            float* dst = g.C + (size_t)row * g.ldc + n;
+            if (atomic) {
+                for (int e = 0; e < 4; ++e) if (n + e < g.N) atomicAdd(dst + e, xs[e] * sc);
+                continue;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float y = xs[e] * sc;
+                if (n + e < g.N) {
+                    if (g.bias) y += g.bias[n + e];
+                    if (g.bias2) y += g.bias2[n + e];
+                    if (g.res) y += g.res[(size_t)row * g.ldr + n + e];
+                }
+                if (g.act) y = y > 0.f ? y : y * g.slope;
+                xs[e] = y;
+            }
+            if (vec_ok && n + 3 < g.N) *(float4*)dst = make_float4(xs[0], xs[1], xs[2], xs[3]);
+            else for (int e = 0; e < 4; ++e) if (n + e < g.N) dst[e] = xs[e];
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_d), "r"(TMEM_COLS) : "memory");
+}
+
 }  // namespace
 
 // launched by d3f_gemm_launch (gemm.cu) with the split decision already made
 // tcgen05 kernel variant: 0 = tc5 (register-fed, one stage, 3-4 CTAs/SM), 1 = tc6 (A through a cp.async ring; needs a
 // 16-byte aligned A), 2 = tc7 (warp-specialised, two operand stages).  Default from D3F_GEMM_PIPELINE = reg | cpasync | ws.
 static int g_tc_pipeline = -1;
-extern "C" void d3f_set_gemm_pipeline(int variant) { g_tc_pipeline = variant < 0 ? -1 : (variant > 2 ? 2 : variant); }
+extern "C" void d3f_set_gemm_pipeline(int variant) { g_tc_pipeline = variant < 0 ? -1 : (variant > 3 ? 3 : variant); }
 static int tc_pipeline() {
     if (g_tc_pipeline < 0) {
         const char* e = getenv("D3F_GEMM_PIPELINE");
-        g_tc_pipeline = !e ? D3F_GEMM_PIPELINE_DEFAULT : (e[0] == 'r' ? 0 : (e[0] == 'c' ? 1 : 2));
+        g_tc_pipeline = !e ? D3F_GEMM_PIPELINE_DEFAULT : (e[0] == 'r' ? 0 : (e[0] == 'c' ? 1 : (e[0] == 't' ? 3 : 2)));
     }
     return g_tc_pipeline;
 }
@@ -850,6 +1130,17 @@ static int launch_bn(const D3fGemm& g, int splits, cudaStream_t stream) {
         return D3F_OK;
     }
     if constexpr (BN <= 64) {
+        if (tc_pipeline() == 3) {    // experimental: A operand in tensor memory
+            static bool attr8_set = false;
+            if (!attr8_set) {
+                D3F_CHECK_CUDA(cudaFuncSetAttribute(tc8_gemm_kernel<TA, TB, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    Cfg8<BN>::SMEM_BYTES));
+                attr8_set = true;
+            }
+            tc8_gemm_kernel<TA, TB, BN><<<grid, NT8, Cfg8<BN>::SMEM_BYTES, stream>>>(g);
+            D3F_CHECK_LAUNCH();
+            return D3F_OK;
+        }
         if (tc_pipeline() == 2) {
             static bool attr7_set = false;
             if (!attr7_set) {
@@ -877,7 +1168,7 @@ template <bool TA, bool TB>
 static int launch_mode(const D3fGemm& g, int splits, cudaStream_t stream) {
     if (g.N <= 32) return launch_bn<TA, TB, 32>(g, splits, stream);
     // wide outputs with enough row tiles to fill the chip: 128-wide tiles halve the A re-reads
-    if (tc_pipeline() != 2 && g.N >= 256 && d3f_ceil_div(g.M, BM) * d3f_ceil_div(g.N, 128) * splits >= 148)
+    if (tc_pipeline() < 2 && g.N >= 256 && d3f_ceil_div(g.M, BM) * d3f_ceil_div(g.N, 128) * splits >= 148)
         return launch_bn<TA, TB, 128>(g, splits, stream);
     return launch_bn<TA, TB, 64>(g, splits, stream);
 }

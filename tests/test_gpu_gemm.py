@@ -8,14 +8,23 @@ from _util import rel_err
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["tcgen05-reg", "tcgen05-cpasync", "tcgen05-ws", "mma"])
+import os
+
+# the A-operand-in-tensor-memory variant (tc8) was written after the last GPU run of round 1: it is exercised only on
+# request (D3F_TEST_EXPERIMENTAL=1) until it has been validated on hardware
+_GEMM_IMPLS = ["tcgen05-reg", "tcgen05-cpasync", "tcgen05-ws", "mma"] + (
+    ["tcgen05-tmem"] if os.environ.get("D3F_TEST_EXPERIMENTAL") == "1" else [])
+
+
+@pytest.fixture(params=_GEMM_IMPLS)
 def gemm_impl(request, cuda):
     """tcgen05-reg = register-fed one-stage kernel, tcgen05-cpasync = A through a cp.async ring (where A is 16-byte
-    aligned), tcgen05-ws = warp-specialised two-stage kernel, mma = legacy mma.sync kernel."""
+    aligned), tcgen05-ws = warp-specialised two-stage kernel, tcgen05-tmem = A operand in tensor memory (experimental),
+    mma = legacy mma.sync kernel."""
     from d3feat.pytorch_b200 import _lib
     lib = _lib.load()
     lib.d3f_set_gemm_impl(0 if request.param == "mma" else 1)
-    lib.d3f_set_gemm_pipeline({"tcgen05-reg": 0, "tcgen05-cpasync": 1, "tcgen05-ws": 2}.get(request.param, -1))
+    lib.d3f_set_gemm_pipeline({"tcgen05-reg": 0, "tcgen05-cpasync": 1, "tcgen05-ws": 2, "tcgen05-tmem": 3}.get(request.param, -1))
     yield request.param
     if request.param != "mma":
         assert lib.d3f_gemm_tcgen05_failed() == 0, "a tcgen05 GEMM gave up waiting on its mbarrier"

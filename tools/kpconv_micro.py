@@ -76,7 +76,7 @@ for (M, N, K, ta, tb) in shapes:
     a = torch.randn((K, M) if ta else (M, K), device=dev)
     b = torch.randn((N, K) if tb else (K, N), device=dev)
     row = []
-    for pipe in (0, 1, 2):
+    for pipe in (0, 1, 2):      # (3 = experimental TMEM-A variant: add once validated)
         lib.d3f_set_gemm_pipeline(pipe)
         for det in (False, True):
             row.append(timed(lambda: ops.gemm(a, b, ta, tb, deterministic=det)))
