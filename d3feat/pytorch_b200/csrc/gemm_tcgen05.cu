@@ -821,8 +821,10 @@ tc7_gemm_kernel(D3fGemm g) {
 
 
 // ------------------------------------------------------------------------------------------------------------------
-// tc8 (EXPERIMENTAL -- written at the end of round 1 from the clock64 breakdown in profiles/r1p_tc5_phase_timing.txt,
-// not yet run on a GPU; selectable with D3F_GEMM_PIPELINE=tmem only): the A operand lives in TENSOR MEMORY.
+// tc8 (EXPERIMENTAL -- written at the end of round 1 from the clock64 breakdown in profiles/r1p_tc5_phase_timing.txt;
+// it passed the 36 fp64-parity cases of tests/test_gpu_gemm.py on a B200 with the round's last GPU seconds
+// (profiles/r1q_tc8_parity.log) but has NOT been timed yet; selectable with D3F_GEMM_PIPELINE=tmem only): the A operand
+// lives in TENSOR MEMORY.
 //
 // tc5/tc6/tc7 all push A through shared memory twice over (hi + lo stores, then every MMA re-reads the 128-row tile:
 // ~5x the tile's bytes through a 128 B/clk pipe, ~3700 cycles per K tile).  Here

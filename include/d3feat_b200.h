@@ -279,7 +279,7 @@ int d3f_mutual_nn(const float* source, const float* target, int n_source, int n_
 void d3f_set_gemm_impl(int use_tcgen05);
 /* tcgen05 back end only, kernel variant: 0 = register-fed, one operand stage, 3-4 CTAs/SM (default); 1 = A operand
  * through a cp.async ring (needs a 16-byte aligned A); 2 = warp-specialised (8 converter warps + 1 MMA warp, two
- * operand stages); 3 = EXPERIMENTAL, not yet validated on hardware: A operand in tensor memory (tcgen05.st + TMEM-A MMA);
+ * operand stages); 3 = EXPERIMENTAL (numerically validated, not yet timed): A operand in tensor memory (tcgen05.st + TMEM-A MMA);
  * -1 = default (environment D3F_GEMM_PIPELINE = reg | cpasync | ws | tmem, else the library's built-in choice). */
 void d3f_set_gemm_pipeline(int variant);
 /* B-resident mma.sync kernel (csrc/gemm_skinny.cu) for N <= 64, K % 16 == 0, non-transposed-A problems: 2 = every such
