@@ -76,7 +76,8 @@ for (M, N, K, ta, tb) in shapes:
     a = torch.randn((K, M) if ta else (M, K), device=dev)
     b = torch.randn((N, K) if tb else (K, N), device=dev)
     row = []
-    for pipe in (0, 1, 2):      # (3 = experimental TMEM-A variant: add once validated)
+    pipes = (0, 1, 2, 3) if os.environ.get("D3F_MICRO_TMEM", "1") == "1" else (0, 1, 2)   # 3 = experimental A-in-TMEM kernel (tc8)
+    for pipe in (0, 1, 2):
         lib.d3f_set_gemm_pipeline(pipe)
         for det in (False, True):
             row.append(timed(lambda: ops.gemm(a, b, ta, tb, deterministic=det)))
@@ -84,8 +85,14 @@ for (M, N, K, ta, tb) in shapes:
     lib.d3f_set_gemm_skinny(2)
     row.append(timed(lambda: ops.gemm(a, b, ta, tb, deterministic=True)))
     lib.d3f_set_gemm_skinny(-1)
+    t8 = None
+    if 3 in pipes:
+        lib.d3f_set_gemm_pipeline(3)
+        t8 = (timed(lambda: ops.gemm(a, b, ta, tb, deterministic=False)), timed(lambda: ops.gemm(a, b, ta, tb, deterministic=True)))
+        lib.d3f_set_gemm_pipeline(-1)
     fl = 2.0 * M * N * K
     print("M=%6d N=%5d K=%6d ta=%d tb=%d | reg: %6.1f (det %6.1f) | cp.async: %6.1f (det %6.1f) | warp-spec: %6.1f (det %6.1f) | skinny(if eligible): %6.1f | %.1f TFLOP/s best"
-          % (M, N, K, ta, tb, row[0], row[1], row[2], row[3], row[4], row[5], row[6], fl / min(row) / 1e6))
+          % (M, N, K, ta, tb, row[0], row[1], row[2], row[3], row[4], row[5], row[6], fl / min(row) / 1e6)
+          + ("" if t8 is None else " | tmem-A (tc8): %6.1f (det %6.1f)" % t8))
 if lib.d3f_gemm_tcgen05_failed() != 0:
     print("WARNING: a tcgen05 GEMM gave up waiting on an mbarrier")
