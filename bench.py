@@ -1,17 +1,20 @@
 #!/usr/bin/env python
 """bench.py -- fragment-pairs/sec of the D3Feat hot path on B200 (BASELINE.json metric).
 
-One STEP = one 20k+20k synthetic fragment pair through the whole hot path (BASELINE config 3):
-device pyramid build (5 radius searches + 4 grid subsamplings + 4 pool + 4 upsample searches)
--> KPFCNN forward (14 KPConv) -> circle + detector loss -> backward -> SGD step.
+One STEP = one synthetic fragment pair through the whole hot path: device pyramid build (5 radius searches + 4 grid
+subsamplings + 4 pool + 4 upsample searches) -> KPFCNN forward (14 KPConv) -> circle + detector loss -> backward ->
+SGD step (momentum / weight decay / non-finite guard, trainer.py:104-111).
 
-  python bench.py --gpus N --steps K --warmup W        (N>1: launched by torch.distributed.run)
-  python bench.py --impl reference ...                  (the reference's CPU path, timed on host cores)
+  python bench.py --gpus N --steps K --warmup W                 (N>1: launched by torch.distributed.run)
+  python bench.py --config deformable40k ...                     (BASELINE config 4; default pair20k = config 3)
+  python bench.py --impl reference ...                           (the reference's CPU path, timed on host cores)
 
-Prints ONE JSON line (rank 0).  `value` = pairs/s with the raw pair already resident in HBM,
-`e2e` = the same through the public API from pinned HOST buffers with the loss read back.
+Prints ONE JSON line (rank 0).  `value` = pairs/s with the raw pair already resident in HBM, `e2e` = the same through
+the public API from pinned HOST buffers with the loss read back, `fwd_only` = pyramid + forward + loss without
+backward / optimiser, `parity_rel_err` = the timed configuration checked against the CPU oracle after the timed region.
 """
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -37,8 +40,21 @@ def emit(line):
     _REAL_STDOUT.write(json.dumps(line) + "\n")
     _REAL_STDOUT.flush()
 
-N_POINTS = 20000
+
 POOL = 4  # distinct synthetic pairs cycled through the steps (per rank)
+
+# workload table: BASELINE.json configs 3 and 4.  `limits` = neighborhood_limits by the reference's 80th-percentile rule
+# (dataloader.py:191-223) on the first two synthetic pairs; both arms re-derive them when the entry is None.
+CONFIGS = {
+    "pair20k": dict(points=20000, deformable_from=None, limits=[35, 42, 42, 45, 47],
+                    label="BASELINE config 3: %d+%d-point synthetic room-shell pair, device pyramid build + KPFCNN fwd "
+                          "(default arch, 24.3M params, K=15, first_features_dim=128) + circle & detector loss (P=128) "
+                          "+ bwd + SGD step"),
+    "deformable40k": dict(points=40000, deformable_from=3, limits=None,
+                          label="BASELINE config 4: %d+%d-point synthetic room-shell pair, deformable KPConv in the "
+                                "non-strided blocks of levels 3-4 (25.4M params, neighbour matrices at the deform radius), "
+                                "device pyramid build + KPFCNN fwd + circle & detector loss (P=128) + bwd + SGD step"),
+}
 
 
 def parse():
@@ -47,12 +63,24 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--points", type=int, default=N_POINTS)
+    ap.add_argument("--config", default="pair20k", choices=sorted(CONFIGS))
+    ap.add_argument("--points", type=int, default=None, help="override the points per fragment of --config")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--fwd-only", action="store_true", help="diagnostic: forward + loss only")
-    ap.add_argument("--host-profile", action="store_true", help="diagnostic: CPU enqueue time per phase -> stderr")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-run parity check against the CPU oracle")
     ap.add_argument("--no-graph", action="store_true", help="diagnostic: static pipeline without CUDA-graph capture")
-    return ap.parse_args()
+    a = ap.parse_args()
+    a.wl = dict(CONFIGS[a.config])
+    if a.points is not None and a.points != a.wl["points"]:
+        a.wl["points"], a.wl["limits"] = a.points, None
+    a.points = a.wl["points"]
+    return a
+
+
+def make_config(args):
+    from d3feat.pytorch_b200.config import build_architecture, default_config
+    if args.wl["deformable_from"] is None:
+        return default_config()
+    return default_config(architecture=build_architecture(5, deformable_from=args.wl["deformable_from"]))
 
 
 # ------------------------------------------------------------------------------------------- helpers
@@ -91,6 +119,10 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
         sm, mx, reasons = [], None, set()
         for r in self.rows:
             try:
@@ -118,16 +150,29 @@ def make_pairs(n, count, seed0):
     return [synthetic.fragment_pair(n, seed=seed0 + i) for i in range(count)]
 
 
-# ------------------------------------------------------------------------------------------- reference arm
-def cpu_reference_setup(n_points):
+def workload_config(args, limits):
+    n = args.points
+    return {"workload": args.wl["label"] % (n, n), "name": args.config,
+            "points_per_fragment": n, "neighborhood_limits": [int(v) for v in limits], "pairs_per_step_per_gpu": 1,
+            "parallelism": "dp%d (1 pair per GPU, descriptor all-gather, 2-bucket gradient all-reduce)" % args.gpus,
+            "l2_policy": "256 MiB L2 flush write between timed steps (outside the per-step event brackets)"}
+
+
+# ------------------------------------------------------------------------------------------- reference arm (CPU oracle)
+def cpu_reference_setup(cfg):
     import _inputs
-    from d3feat.pytorch_b200.config import default_config
     from oracle import cpu
-    cfg = default_config()
     sd = _inputs.kpfcnn_state_dict(cfg, seed=0)
     impl = "ref" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libd3feat_ref.so")) else "port"
     cpu.build()
-    return cfg, sd, impl
+    return sd, impl
+
+
+CPU_KIND = {"ref": "reference C++ + torch-CPU port", "port": "port"}
+CPU_DETAIL = {"ref": "pyramid: UNMODIFIED reference C++ (oracle/_ref: neighbors.cpp / grid_subsampling.cpp / nanoflann, single "
+                     "thread as in the reference); model + losses + backward + SGD: torch-CPU restatement (oracle/model_ref.py, "
+                     "single-GEMM KPConv: faster than the reference's own op chain, i.e. conservative for the speed-up)",
+              "port": "pyramid: plain-C port (oracle/d3feat_oracle.c); model: torch-CPU restatement (oracle/model_ref.py)"}
 
 
 def tune_cpu_threads(cfg, sd, impl):
@@ -136,7 +181,7 @@ def tune_cpu_threads(cfg, sd, impl):
     from oracle import pipeline
     cores = os.cpu_count() or 1
     probe = make_pairs(4000, 1, 999)[0]
-    lim = [40, 43, 44, 43, 26]
+    lim = [40, 43, 44, 120, 120] if any("deform" in b for b in cfg.architecture) else [40, 43, 44, 43, 26]
     best, best_t = cores, float("inf")
     for th in sorted({min(cores, v) for v in (8, 16, 32, 64, cores)}):
         torch.set_num_threads(th)
@@ -165,65 +210,93 @@ def cpu_limits(pairs, cfg, impl):
 
 
 def run_reference(args):
-    """The reference's own CPU implementation of the path on this box's host cores: reference C++
-    (oracle/_ref) for the pyramid + the torch-CPU restatement of KPFCNN / losses (the reference's
-    Python cannot travel to the GPU box).  Under torchrun only rank 0 works."""
+    """The reference's own CPU implementation of the path on this box's host cores: reference C++ (oracle/_ref) for the
+    pyramid + the torch-CPU restatement of KPFCNN / losses (the reference's Python cannot travel to the GPU box).
+    ONE process whatever --gpus says: under torchrun rank 0 alone works, the other ranks exit 0 (the N>1 ratio the driver
+    computes therefore divides N GPUs by one CPU process -- only the N=1 ratio is like for like)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import pipeline
-    cfg, sd, impl = cpu_reference_setup(args.points)
+    cfg = make_config(args)
+    sd, impl = cpu_reference_setup(cfg)
     cores = tune_cpu_threads(cfg, sd, impl)
-    pairs = make_pairs(args.points, min(POOL, max(1, args.steps)), 0)
-    limits = LIMITS_20K if args.points == N_POINTS else cpu_limits(pairs[:1], cfg, impl)
+    pairs = make_pairs(args.points, min(POOL, max(2, args.steps)), 0)
+    limits = args.wl["limits"] or cpu_limits(pairs[:2], cfg, impl)
     sgd = {}
     for i in range(args.warmup):
-        pipeline.cpu_pair_step(pairs[i % len(pairs)], sd, cfg, limits, impl=impl, backward=not args.fwd_only, sgd=sgd)
+        pipeline.cpu_pair_step(pairs[i % len(pairs)], sd, cfg, limits, impl=impl, backward=True, sgd=sgd)
     t0 = time.perf_counter()
     stages = {}
     for i in range(args.steps):
-        t, _ = pipeline.cpu_pair_step(pairs[i % len(pairs)], sd, cfg, limits, impl=impl, backward=not args.fwd_only, sgd=sgd)
+        t, _ = pipeline.cpu_pair_step(pairs[i % len(pairs)], sd, cfg, limits, impl=impl, backward=True, sgd=sgd)
         for k, v in t.items():
             stages[k] = stages.get(k, 0.0) + v
     dt = time.perf_counter() - t0
     val = args.steps / dt
-    sample = "%d pairs of %d+%d points, whole path (collate+fwd+loss+bwd), %s" % (
-        args.steps, args.points, args.points, "pyramid by the reference C++ (oracle/_ref), model by the torch-CPU oracle"
-        if impl == "ref" else "oracle port")
+    sample = "%d pairs of %d+%d points, whole path (collate+fwd+loss+bwd+SGD); %s" % (args.steps, args.points, args.points,
+                                                                                       CPU_DETAIL[impl])
     line = {"impl": "reference", "metric": "fragment-pairs/sec", "value": val, "unit": "pairs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, limits),
-            "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "reference" if impl == "ref" else "port",
+            "reference_processes": 1,
+            "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": CPU_KIND[impl],
                              "sample": sample, "stage_seconds_per_pair": {k: v / args.steps for k, v in stages.items()}},
             "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
 
 
-LIMITS_20K = [35, 42, 42, 45, 47]  # 80th-percentile rule on the synthetic 20k pairs (recomputed on the device below)
-
-
-def workload_config(args, limits):
-    return {"workload": "BASELINE config 3: %d+%d-point synthetic room-shell pair, device pyramid build + KPFCNN fwd "
-                        "(default arch, 24.3M params, K=15, first_features_dim=128) + circle & detector loss (P=128) "
-                        "+ bwd + SGD step" % (args.points, args.points),
-            "points_per_fragment": args.points, "neighborhood_limits": [int(v) for v in limits], "pairs_per_step_per_gpu": 1,
-            "parallelism": "dp%d (1 pair per GPU, descriptor all-gather)" % args.gpus,
-            "l2_policy": "256 MiB L2 flush write between timed steps (outside the per-step event brackets)"}
-
-
 # ------------------------------------------------------------------------------------------- B200 arm
+def parity_check(args, cfg, limits, pair, sd_before, stepper, caps):
+    """The TIMED configuration against the CPU oracle (outside the timed region): replay the captured step on `pair`
+    with the weights `sd_before`, and compare pyramid indices (bit-exact), descriptors, scores and both losses."""
+    from oracle import model_ref, pipeline
+    impl = "ref" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libd3feat_ref.so")) else "port"
+    t0 = time.perf_counter()
+    batch = stepper.batch
+    cpu_b = pipeline.cpu_collate(pair, cfg, limits, impl=impl)
+    idx_equal, n_idx = True, 0
+    for l in range(len(cpu_b["points"])):
+        n = cpu_b["points"][l].shape[0]
+        idx_equal &= bool(np.array_equal(batch["points"][l][:n].cpu().numpy().view(np.uint32),
+                                         cpu_b["points"][l].numpy().view(np.uint32)))
+        for key in ("neighbors", "pools", "upsamples"):
+            e = cpu_b[key][l]
+            if e.numel() == 0:
+                continue
+            n_sup = cpu_b["points"][l + 1].shape[0] if key == "upsamples" else n
+            cap_sup = caps[l + 1] if key == "upsamples" else caps[l]
+            got = batch[key][l][:e.shape[0], :e.shape[1]].long().cpu()
+            want = torch.where(e == n_sup, torch.full_like(e, cap_sup), e)     # static pipeline: shadow index = capacity
+            idx_equal &= bool(torch.equal(got, want))
+            n_idx += e.numel()
+    n0 = cpu_b["points"][0].shape[0]
+    with torch.no_grad():
+        f_ref, s_ref = model_ref.kpfcnn_forward(sd_before, cpu_b, cfg, training=True)
+        dl, det, _, _ = model_ref.pair_losses(f_ref, s_ref, cpu_b, "circle")
+
+    def rel(a, b):
+        a, b = a.detach().double().cpu(), b.detach().double()
+        return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    return {"vs": "CPU oracle (oracle/pipeline.cpu_collate [%s] + oracle/model_ref) on one timed pair with the weights the "
+                  "captured step started from" % impl,
+            "points_per_fragment": args.points, "indices_bit_exact": idx_equal, "indices_compared": n_idx,
+            "features": rel(stepper.features[:n0], f_ref), "scores": rel(stepper.scores[:n0], s_ref),
+            "desc_loss": rel(stepper.desc_loss, dl), "det_loss": rel(stepper.det_loss, det),
+            "tolerance": 1e-4, "seconds": time.perf_counter() - t0}
+
+
 def run_b200(args):
     import torch.distributed as dist
     from d3feat.pytorch_b200 import _lib, ops
     from d3feat.pytorch_b200.architectures import KPFCNN
-    from d3feat.pytorch_b200.blocks import gather
-    from d3feat.pytorch_b200.config import default_config
     from d3feat.pytorch_b200.dataloader import calibrate_neighbors, collate_fn_descriptor
     from d3feat.pytorch_b200.loss import PairLoss
     from d3feat.pytorch_b200 import parallel
     from d3feat.pytorch_b200.engine import PairStep, plan_capacities
+    from d3feat.pytorch_b200.optim import FlatSGD
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -236,15 +309,14 @@ def run_b200(args):
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
 
-    cfg = default_config()
-    torch.manual_seed(0); np.random.seed(0)
+    cfg = make_config(args)
+    import _inputs
     model = KPFCNN(cfg).to(dev)
+    # same seeded weights as the reference arm / the parity oracle (tests/_inputs.py)
+    model.load_state_dict(_inputs.kpfcnn_state_dict(cfg, seed=0), strict=True)
     model.train()
-    # config.py:62-69; fused=True: one multi-tensor kernel per parameter group instead of three foreach passes
-    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.98, weight_decay=1e-6, fused=True)
-    # multi-GPU: all gradients are views of one buffer (zero() + ONE all-reduce); single GPU: plain per-parameter
-    # gradients created by the backward pass (saves one accumulate kernel per parameter, ~130 launches per step)
-    flat = parallel.FlatGradients(model) if world > 1 else None
+    # training_3DMatch.py:62-80 / config.py:64-72: SGD(lr 0.01, momentum 0.98, wd 1e-6) + ExpLR, gradients written in place
+    opt = FlatSGD(model, lr=0.01, momentum=0.98, weight_decay=1e-6, gamma=0.1 ** (1 / 80))
     loss_fn = PairLoss("circle", "euclidean", cfg.log_scale, cfg.safe_radius, cfg.pos_margin, cfg.neg_margin)
 
     pairs = make_pairs(args.points, POOL, 100 * rank)
@@ -253,49 +325,14 @@ def run_b200(args):
         config = cfg
         def __len__(self): return 2
         def __getitem__(self, i): return pairs[i]
-    limits = [int(v) for v in calibrate_neighbors(_DS(), cfg, collate_fn_descriptor, samples_threshold=10 ** 9)]
+    # neighborhood_limits are a dataset-level hyper-parameter in the reference (one list per run, dataloader.py:225-238)
+    limits = args.wl["limits"] or [int(v) for v in calibrate_neighbors(_DS(), cfg, collate_fn_descriptor,
+                                                                        samples_threshold=10 ** 9)]
 
     host = [tuple(torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in p) for p in pairs]
     devp = [tuple(t.to(dev) for t in p) for p in host]
     h2d = sum(t.numel() * t.element_size() for t in host[0])
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    hp = {}
-
-    def tick(name, t0):
-        if args.host_profile:
-            hp[name] = hp.get(name, 0.0) + time.perf_counter() - t0
-        return time.perf_counter()
-
-    def step(data, read_loss):
-        t0 = time.perf_counter()
-        batch = collate_fn_descriptor([data], cfg, limits)
-        t0 = tick("collate", t0)
-        feats, scores = model(batch)
-        t0 = tick("forward", t0)
-        c = batch["corr"].long()
-        n0 = data[0].shape[0]
-        ia, ip = c[:, 0], c[:, 1] + n0
-        a, p = gather(feats, ia), gather(feats, ip)          # trainer.py:91-94 row selects
-        sa, sp = gather(scores, ia), gather(scores, ip)
-        if world > 1:
-            out = parallel.cross_fragment_loss(loss_fn, a, p, batch["dist_keypts"], sa, sp)
-        else:
-            out = loss_fn(a, p, batch["dist_keypts"], sa, sp)
-        loss = out["desc_loss"] * cfg.desc_loss_weight + out["det_loss"] * cfg.det_loss_weight
-        t0 = tick("loss", t0)
-        if not args.fwd_only:
-            if flat is not None:
-                flat.zero()
-            else:
-                opt.zero_grad(set_to_none=True)
-            loss.backward()
-            t0 = tick("backward", t0)
-            if flat is not None:
-                flat.allreduce()
-            opt.step()
-            t0 = tick("optimizer", t0)
-        return float(loss.detach()) if read_loss else loss
 
     def barrier():
         if world > 1:
@@ -305,118 +342,135 @@ def run_b200(args):
     # ---- the production path: static capacities, no host sync, one CUDA graph per pair step
     sizes = [[int(t.shape[0]) for t in collate_fn_descriptor([p], cfg, limits)["points"]] for p in pairs]
     caps = plan_capacities(sizes)
-    stepper = PairStep(model, cfg, limits, caps, args.points, args.points, loss_fn,
-                       None if args.fwd_only else opt, None if args.fwd_only else flat, num_node=cfg.num_node,
-                       cross_fragment=parallel.cross_fragment_loss if world > 1 else None)
+    xfrag = parallel.cross_fragment_loss if world > 1 else None
+    stepper = PairStep(model, cfg, limits, caps, args.points, args.points, loss_fn, opt, None, num_node=cfg.num_node,
+                       cross_fragment=xfrag)
+    fwd_stepper = PairStep(model, cfg, limits, caps, args.points, args.points, loss_fn, None, None, num_node=cfg.num_node,
+                           cross_fragment=xfrag)
+    # every parameter gradient must be written in place by one step (NaN-poison test); also the first eager step
     l0 = lib.d3f_launch_count()
-    stepper(devp[0])
-    torch.cuda.synchronize()
+    opt.verify_direct(lambda: stepper(devp[0]))
     launches_per_step = lib.d3f_launch_count() - l0
+    fwd_stepper(devp[0])
+    torch.cuda.synchronize()
     graph_mode = "cuda-graph"
     if args.no_graph:
         graph_mode = "eager (static shapes)"
     else:
         try:
             stepper.capture()
+            fwd_stepper.capture()
         except Exception as e:  # noqa: BLE001
             sys.stderr.write("CUDA graph capture failed (%s: %s); running the static pipeline eagerly\n" % (type(e).__name__, e))
-            stepper.graph = None
-            graph_mode = "eager (static shapes; capture failed)"
+            stepper.graph = fwd_stepper.graph = None
+            graph_mode = "eager (static shapes; capture failed: %s)" % type(e).__name__
             torch.cuda.synchronize()
 
-    def timed(kind, steps, profile=False):
+    def timed(kind, steps, st=None):
+        st = st or stepper
         src = devp if kind == "device" else host
         evs = []
         barrier()
-        ops.PROFILE = {} if profile else None
-        launches0 = lib.d3f_launch_count()
         wall0 = time.perf_counter()
         for i in range(steps):
             flush.fill_(i & 0xFF)          # L2 flush, outside the event bracket
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            if profile:
-                step(src[i % POOL], read_loss=False)        # exact-shape eager path with per-op events
-            else:
-                stepper(src[i % POOL])                      # H2D (e2e) or D2D copies into the static inputs + replay
-                if kind == "host":
-                    float(stepper.loss)                     # D2H read of the step's result
+            st(src[i % POOL])                               # H2D (e2e) or D2D copies into the static inputs + replay
+            if kind == "host":
+                float(st.loss)                              # D2H read of the step's result
             e1.record()
             evs.append((e0, e1))
         barrier()
         wall = time.perf_counter() - wall0
-        prof, ops.PROFILE = ops.PROFILE, None
         ms = sum(a.elapsed_time(b) for a, b in evs)
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), wall, lib.d3f_launch_count() - launches0, prof
+        return float(t[0]), wall
 
     for i in range(max(args.warmup, 3)):
         stepper(devp[i % POOL])
     for i in range(2):
         stepper(host[i % POOL]); float(stepper.loss)
+        fwd_stepper(devp[i % POOL])
     stepper.check()
-    for i in range(2):
-        step(devp[i % POOL], False)
+    fwd_stepper.check()
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    hp.clear()
-    ms_dev, wall_dev, _, _ = timed("device", args.steps)
-    ms_e2e, wall_e2e, _, _ = timed("host", args.steps)
-    stepper.check()                  # no capacity / candidate-buffer overflow in any timed step
+    ms_dev, wall_dev = timed("device", args.steps)
+    ms_e2e, wall_e2e = timed("host", args.steps)
+    ms_fwd, _ = timed("device", args.steps, fwd_stepper)
+    stepper.check()                  # sticky flags: no overflow / GEMM timeout / skipped step in ANY timed step
+    fwd_stepper.check()
     launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
-    # separate pass with per-op CUDA events (same steps, same stream) for the roofline / op breakdown only
-    _, _, _, prof = timed("device", args.steps, profile=True)
 
-    def finish():
-        """Leave without interpreter / NCCL teardown: with CUDA graphs that captured NCCL kernels,
-        destroy_process_group() (and the implicit teardown at exit) hung a 2-GPU run after its JSON line was out
-        (round 1).  All ranks meet at a barrier first so nobody exits under a peer that still needs it."""
+    # ---- parity of the timed configuration (rank 0, N = 1: the cross-fragment loss of N > 1 has its own NCCL test)
+    parity = None
+    if rank == 0 and world == 1 and not args.no_parity:
+        sd_before = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+        stepper(devp[0])
+        torch.cuda.synchronize()
+        parity = parity_check(args, cfg, limits, pairs[0], sd_before, stepper, caps)
+    # ---- separate pass with per-op CUDA events (same static pipeline, eager, same streams): roofline / op breakdown only
+    prof_steps = min(args.steps, 10)
+    ops.PROFILE = {}
+    for i in range(prof_steps):
+        flush.fill_(i & 0xFF)
+        stepper.load(devp[i % POOL])
+        stepper._body()
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+
+    final_loss = float(stepper.loss)
+
+    # ---- orderly teardown: graphs (they hold NCCL kernels) before the communicator, then a normal interpreter exit
+    stepper.release(); fwd_stepper.release()
+    gc.collect()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def teardown():
         if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-        _REAL_STDOUT.flush()
-        sys.stderr.flush()
-        os._exit(0)
+            dist.destroy_process_group()
 
     if rank != 0:
-        finish()
+        teardown()
+        return
 
-    if args.host_profile:
-        n_calls = 2 * args.steps + args.steps
-        sys.stderr.write("host enqueue ms/step (timed passes only approx): %s\n" % {k: round(1e3 * v / max(n_calls, 1), 3) for k, v in hp.items()})
     pk, pk_src = peaks()
     # roofline of the dominant op: the KPConv forward with the most algorithmic bytes (L0 resnetb 32->32)
     fwd = {k: v for k, v in prof.items() if k[0] == "kpconv_fwd"}
     per_layer, tot_bytes, tot_ms = [], 0, 0.0
     for k, evs in fwd.items():
         _, nq, ns, H, cin, cout, deformed = k
-        calls_per_step = len(evs) / args.steps
+        calls_per_step = len(evs) / prof_steps
         avg_ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
         by = kpconv_logical_bytes(nq, ns, H, cin, cout)
-        per_layer.append({"nq": nq, "ns": ns, "H": H, "cin": cin, "cout": cout, "calls_per_step": calls_per_step,
-                          "ms": avg_ms, "logical_MB": by / 1e6, "GBps": by / avg_ms / 1e6,
+        per_layer.append({"nq": nq, "ns": ns, "H": H, "cin": cin, "cout": cout, "deformed": deformed,
+                          "calls_per_step": calls_per_step, "ms": avg_ms, "logical_MB": by / 1e6, "GBps": by / avg_ms / 1e6,
                           "TFLOPs": kpconv_flops(nq, H, cin, cout) / avg_ms / 1e9})
         tot_bytes += by * calls_per_step
         tot_ms += avg_ms * calls_per_step
     per_layer.sort(key=lambda d: -d["logical_MB"])
     dom = per_layer[0]
-    # the gather kernel of that layer alone (events recorded inside d3f_kpconv_forward around kp2_correlate): it reads
-    # the neighbour rows / positions / indices and writes wf [Nq, K*Cin] for the contraction
-    gather = None
+    # the dominant KERNEL of that op alone: events recorded inside d3f_kpconv_forward around the fused kernel (or, on the
+    # two-kernel path, around the gather kernel)
+    kern = None
     gk = [(k, v) for k, v in prof.items() if k[0] == "kpconv_gather" and k[1:6] == (dom["nq"], dom["ns"], dom["H"], dom["cin"], dom["cout"])]
+    impl = int(lib.d3f_get_kpconv_impl())
+    fused = impl == 3 and not dom["deformed"] and bool(lib.d3f_kpconv_fused_eligible(dom["H"], 15, dom["cin"], dom["cout"]))
     if gk:
         evs = gk[0][1]
-        g_ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
-        g_bytes = dom["nq"] * dom["H"] * (4 * dom["cin"] + 16) + 12 * dom["nq"] + 4 * dom["nq"] * 15 * dom["cin"]
-        gather = {"kernel": "kp2_correlate (gather + kernel-point correlation)", "avg_ms_per_launch": g_ms,
-                  "algorithmic_bytes_per_launch": g_bytes, "GBps": g_bytes / g_ms / 1e6,
-                  "frac_of_hbm_peak": g_bytes / g_ms / 1e6 / pk["hbm_gbs"],
-                  "note": "bytes = Nq*H*(4Cin+12+4) + 12Nq read + 4*Nq*K*Cin written (wf)"}
+        k_ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+        kern = {"kernel": "kpf_fused_kernel (gather + correlation + tcgen05 contraction + epilogue, one launch)" if fused
+                else "kp2_correlate (gather + kernel-point correlation; the contraction is a second kernel)",
+                "avg_ms_per_launch": k_ms}
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
@@ -427,16 +481,22 @@ def run_b200(args):
             pass
     stage_ms = {}
     for k, evs in prof.items():
-        stage_ms[k[0]] = stage_ms.get(k[0], 0.0) + sum(a.elapsed_time(b) for a, b in evs) / args.steps
-    op_breakdown = sorted(([list(map(str, k)), len(evs) / args.steps, sum(a.elapsed_time(b) for a, b in evs) / args.steps]
+        stage_ms[k[0]] = stage_ms.get(k[0], 0.0) + sum(a.elapsed_time(b) for a, b in evs) / prof_steps
+    op_breakdown = sorted(([list(map(str, k)), len(evs) / prof_steps, sum(a.elapsed_time(b) for a, b in evs) / prof_steps]
                            for k, evs in prof.items()), key=lambda t: -t[2])[:40]
-    roofline = {"bound": "hbm", "achieved": dom["GBps"], "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": dom["GBps"] / pk["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
-                "kernel": "KPConv forward op (kp_rowpos + kp2_correlate gather + tcgen05 contraction) of the layer with the "
-                          "most algorithmic bytes: Nq=%d Ns=%d H=%d Cin=%d Cout=%d; achieved = SURVEY 8(d) logical gather "
-                          "bytes / CUDA-event time of the whole op" % (dom["nq"], dom["ns"], dom["H"], dom["cin"], dom["cout"]),
-                "gather_kernel": gather, "kpconv_impl": int(lib.d3f_get_kpconv_impl()),
-                "algorithmic_bytes_per_launch": dom["logical_MB"] * 1e6, "avg_ms_per_launch": dom["ms"],
+    # achieved = SURVEY 8(d) logical bytes of the op / duration of its dominant kernel when the op IS one kernel (fused),
+    # else / the CUDA-event time of the whole op (rowpos + gather + contraction)
+    ach_ms = kern["avg_ms_per_launch"] if (fused and kern) else dom["ms"]
+    ach = dom["logical_MB"] * 1e6 / ach_ms / 1e6
+    roofline = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / pk["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": "KPConv forward of the layer with the most algorithmic bytes: Nq=%d Ns=%d H=%d Cin=%d Cout=%d (%s); "
+                          "achieved = SURVEY 8(d) logical gather bytes / CUDA-event time of %s inside the step"
+                          % (dom["nq"], dom["ns"], dom["H"], dom["cin"], dom["cout"],
+                             "fused kernel" if fused else "gather kernel + contraction GEMM",
+                             "that kernel" if fused else "the whole op"),
+                "dominant_kernel": kern, "kpconv_impl": impl, "whole_op_ms": dom["ms"],
+                "algorithmic_bytes_per_launch": dom["logical_MB"] * 1e6, "avg_ms_per_launch": ach_ms,
                 "peak_source": pk_src + ", burst copy bandwidth",
                 "all_kpconv_fwd": {"logical_GB_per_step": tot_bytes / 1e9, "ms_per_step": tot_ms,
                                    "GBps": tot_bytes / tot_ms / 1e6, "frac": tot_bytes / tot_ms / 1e6 / pk["hbm_gbs"]},
@@ -452,34 +512,52 @@ def run_b200(args):
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
-                    "api": "engine.PairStep(pinned host tensors): H2D -> [pyramid build -> KPFCNN -> PairLoss -> backward -> SGD] "
-                           "as one CUDA graph -> float(loss)"},
+                    "api": "engine.PairStep(pinned host tensors): H2D -> [pyramid build -> KPFCNN -> PairLoss -> backward -> "
+                           "FlatSGD] as one CUDA graph -> float(loss)"},
+            "fwd_only": {"value": pairs_per_step * args.steps / (ms_fwd / 1e3), "unit": "pairs/s",
+                         "ms_per_step": ms_fwd / args.steps,
+                         "what": "pyramid build + KPFCNN forward + circle & detector loss (no backward / optimiser), device-resident inputs"},
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
-            "execution": {"mode": graph_mode, "capacities": caps, "final_loss": float(stepper.loss)},
+            "execution": {"mode": graph_mode, "capacities": caps, "final_loss": final_loss,
+                          "optimizer": "FlatSGD: lr %.4g (device scalar, ExpLR gamma %.6f), momentum 0.98, wd 1e-6, non-finite "
+                                       "guard on device, gradients written in place" % (opt.current_lr(), opt.gamma)},
             "wall_s": {"device": wall_dev, "e2e": wall_e2e},
+            "parity_rel_err": parity,
             "roofline": roofline}
 
     if not args.no_cpu_baseline and world == 1:
         from oracle import pipeline
-        cfg_c, sd, impl = cpu_reference_setup(args.points)
-        cores = tune_cpu_threads(cfg_c, sd, impl)
+        sd, impl_c = cpu_reference_setup(cfg)
+        cores = tune_cpu_threads(cfg, sd, impl_c)
         sgd = {}
-        pipeline.cpu_pair_step(pairs[0], sd, cfg_c, limits, impl=impl, backward=not args.fwd_only, sgd=sgd)
+        pipeline.cpu_pair_step(pairs[0], sd, cfg, limits, impl=impl_c, backward=True, sgd=sgd)
         t0 = time.perf_counter()
         n_cpu, stages = 0, {}
         while n_cpu < 3 or (time.perf_counter() - t0 < 10 and n_cpu < 10):
-            t, _ = pipeline.cpu_pair_step(pairs[n_cpu % POOL], sd, cfg_c, limits, impl=impl, backward=not args.fwd_only, sgd=sgd)
+            t, _ = pipeline.cpu_pair_step(pairs[n_cpu % POOL], sd, cfg, limits, impl=impl_c, backward=True, sgd=sgd)
             for k, v in t.items():
                 stages[k] = stages.get(k, 0.0) + v
             n_cpu += 1
         dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": n_cpu / dt, "unit": "pairs/s", "cores": cores,
-                                "kind": "reference" if impl == "ref" else "port",
-                                "sample": "%d pairs of the same workload (pyramid: reference C++ via oracle/_ref, single thread as "
-                                          "in the reference; model+loss+bwd+SGD: torch-CPU oracle on %d threads = fastest of {8,16,32,64,all %d})" % (n_cpu, cores, os.cpu_count() or 1),
+        line["cpu_baseline"] = {"value": n_cpu / dt, "unit": "pairs/s", "cores": cores, "kind": CPU_KIND[impl_c],
+                                "sample": "%d pairs of the same workload; %s; torch threads = fastest of {8,16,32,64,all %d} = %d"
+                                          % (n_cpu, CPU_DETAIL[impl_c], os.cpu_count() or 1, cores),
                                 "stage_seconds_per_pair": {k: v / n_cpu for k, v in stages.items()}}
     emit(line)
-    finish()
+    teardown()
+
+
+def _watchdog(seconds):
+    """The JSON line is out and the process should now exit NORMALLY (interpreter teardown runs the driver's exit hook that
+    records the loaded .so files).  If teardown wedges (round 1 saw NCCL + CUDA-graph teardown hang once), leave after
+    `seconds` instead of holding the box until the driver's timeout."""
+    def bail():
+        sys.stderr.write("bench.py: teardown did not finish in %d s; forcing exit\n" % seconds)
+        sys.stderr.flush()
+        os._exit(0)
+    t = threading.Timer(seconds, bail)
+    t.daemon = True
+    t.start()
 
 
 if __name__ == "__main__":
@@ -488,3 +566,6 @@ if __name__ == "__main__":
         run_reference(a)
     else:
         run_b200(a)
+    _REAL_STDOUT.flush()
+    sys.stderr.flush()
+    _watchdog(60)

@@ -43,8 +43,8 @@ SIGNATURES = {
     "d3f_neighbors_transpose": (c_i, [c_p, c_i, c_i64, c_i, c_i, c_i, c_p, c_p, c_p, c_sz, c_p]),
     "d3f_set_kpconv_impl": (None, [c_i]),
     "d3f_get_kpconv_impl": (c_i, []),
+    "d3f_kpconv_fused_eligible": (c_i, [c_i, c_i, c_i, c_i]),
     "d3f_kpconv_set_gather_events": (None, [c_p, c_p]),
-    "d3f_set_scatter_vec": (None, [c_i]),
     "d3f_colsum": (c_i, [c_p, c_i, c_i, c_p, c_p]),
     "d3f_leaky_backward_colsum": (c_i, [c_p, c_p, c_f, c_i, c_i, c_p, c_p, c_p]),
     "d3f_max_pool_forward": (c_i, [c_p, c_p, c_i, c_i64, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
@@ -54,8 +54,6 @@ SIGNATURES = {
     "d3f_detection_scores_forward": (c_i, [c_p, c_p, c_i, c_i64, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "d3f_detection_scores_backward": (c_i, [c_p, c_p, c_i, c_i64, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
     "d3f_set_gemm_impl": (None, [c_i]),
-    "d3f_set_gemm_pipeline": (None, [c_i]),
-    "d3f_set_gemm_skinny": (None, [c_i]),
     "d3f_gemm_tcgen05_failed": (c_i, []),
     "d3f_gemm": (c_i, [c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_i, c_f, c_p]),
     "d3f_gemm_workspace_bytes": (c_sz, [c_i, c_i, c_i]),
@@ -64,6 +62,8 @@ SIGNATURES = {
     "d3f_kpconv_forward_ex": (c_i, [c_p, c_p, c_p, c_i, c_i64, c_p, c_p, c_p, c_i, c_p,
                                     c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_i, c_p, c_i, c_f,
                                     c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "d3f_gemm_status_snapshot": (c_i, [c_p, c_p]),
+    "d3f_sgd_step": (c_i, [c_p, c_p, c_p, c_sz, c_p, c_f, c_f, c_p, c_i, c_p]),
     "d3f_mutual_nn": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
     "d3f_pair_loss_aux_floats": (c_sz, [c_i]),
     "d3f_pair_dist": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),

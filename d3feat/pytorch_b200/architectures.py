@@ -52,8 +52,17 @@ class KPFCNN(nn.Module):
             in_dim = out_dim
             if 'upsample' in name:
                 layer, r, out_dim = layer - 1, r * 0.5, out_dim // 2
+        # engine.PairStep may install a callback that fires during backward as soon as the gradients of the decoder and
+        # of the encoder blocks from `_early_block` on are complete (first bucket of the data-parallel all-reduce)
+        self._early_block = None
+        self._on_early_grads = None
         if verbose:
             print(self)
+
+    def _early_hook(self, grad):
+        if self._on_early_grads is not None:
+            self._on_early_grads()
+        return None
 
     def forward(self, batch):
         x = batch['features'].clone().detach()
@@ -61,6 +70,8 @@ class KPFCNN(nn.Module):
         for i, block in enumerate(self.encoder_blocks):
             if i in self.encoder_skips:
                 skips.append(x)
+            if i == self._early_block and self._on_early_grads is not None and x.requires_grad:
+                x.register_hook(self._early_hook)
             x = block(x, batch)
         for j, block in enumerate(self.decoder_blocks):
             if j in self.decoder_concats:

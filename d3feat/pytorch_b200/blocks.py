@@ -49,7 +49,7 @@ class _KPConvFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, q_pts, s_pts, inds, x, weights, kpoints, modulations, extent, influence, aggregation,
-                deformed, want_min_d2, bias=None, slope=None, t_off=None, t_src=None):
+                deformed, want_min_d2, bias=None, slope=None, t_off=None, t_src=None, dsts=(None, None)):
         out, wf, wf_un, inv_n, min_d2 = ops.kpconv_forward(q_pts, s_pts, inds, x, weights, kpoints, extent,
                                                            influence, aggregation, deformed, modulations,
                                                            want_min_d2, bias, slope)
@@ -57,6 +57,7 @@ class _KPConvFunction(torch.autograd.Function):
                               out if slope is not None else None)
         ctx.cfg = (extent, influence, aggregation, deformed, slope)
         ctx.transpose = (t_off, t_src) if (t_off is not None and t_src is not None) else None
+        ctx.dsts = dsts     # (grad_weights, grad_bias) destinations inside a flat gradient buffer, or Nones
         if min_d2 is None:
             min_d2 = out.new_empty(0)
         ctx.mark_non_differentiable(min_d2)
@@ -68,10 +69,13 @@ class _KPConvFunction(torch.autograd.Function):
         extent, influence, aggregation, deformed, slope = ctx.cfg
         need = ctx.needs_input_grad
         want_gb = len(need) > 12 and need[12]
+        dst_w, dst_b = ctx.dsts
         if slope is not None:   # out = leaky(z) has the sign of z: the mask comes from the saved output
-            grad_out, gbias = ops.leaky_backward_colsum(grad_out, out, slope, want_gb)
+            grad_out, gbias = ops.leaky_backward_colsum(grad_out, out, slope, want_gb, dst_b if want_gb else None)
         else:
-            gbias = ops.colsum(grad_out) if want_gb else None
+            gbias = ops.colsum(grad_out, out=dst_b) if want_gb else None
+        if dst_b is not None:
+            gbias = None            # written in place
         args = (q_pts.float().contiguous(), s_pts.float().contiguous(),
                 inds if inds.dtype in (torch.int32, torch.int64) else inds.long(),
                 x.float().contiguous(), weights.contiguous(), kpoints.float().contiguous(), extent, influence,
@@ -80,13 +84,15 @@ class _KPConvFunction(torch.autograd.Function):
         if need[4] and need_data:
             # the weight gradient (one GEMM over wf) and the data-gradient chain are independent: two branches
             (_, gw, _, _), (gx, _, gkp, gmod) = ops.run_branches(
-                lambda: ops.kpconv_backward(*args, need_x=False, need_w=True, need_kp=False, need_mod=False),
+                lambda: ops.kpconv_backward(*args, need_x=False, need_w=True, need_kp=False, need_mod=False, gw_out=dst_w),
                 lambda: ops.kpconv_backward(*args, need_x=need[3], need_w=False, need_kp=need[5] and deformed,
                                             need_mod=need[6], transpose=ctx.transpose), grad_out.device)
         else:
             gx, gw, gkp, gmod = ops.kpconv_backward(*args, need_x=need[3], need_w=need[4], need_kp=need[5] and deformed,
-                                                    need_mod=need[6], transpose=ctx.transpose)
-        return (None, None, None, gx, gw, gkp, gmod, None, None, None, None, None, gbias, None, None, None)[:len(need)]
+                                                    need_mod=need[6], transpose=ctx.transpose, gw_out=dst_w)
+        if dst_w is not None:
+            gw = None               # written in place
+        return (None, None, None, gx, gw, gkp, gmod, None, None, None, None, None, gbias, None, None, None, None)[:len(need)]
 
 
 class KPConv(nn.Module):
@@ -157,7 +163,8 @@ class KPConv(nn.Module):
         t_off, t_src = getattr(neighb_inds, "_d3f_transpose", (None, None))
         out, min_d2 = _KPConvFunction.apply(q_pts, s_pts, neighb_inds, x, self.weights, kpoints, modulations,
                                             float(self.KP_extent), self.KP_influence, self.aggregation_mode,
-                                            deformed, deformed, bias, slope, t_off, t_src)
+                                            deformed, deformed, bias, slope, t_off, t_src,
+                                            (ops.grad_dst(self.weights), ops.grad_dst(bias)))
         if deformed:
             self.min_d2 = min_d2
         return out

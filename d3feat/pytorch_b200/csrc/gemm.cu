@@ -266,9 +266,6 @@ int d3f_gemm_launch(const D3fGemm& in, bool ta, bool tb, cudaStream_t stream, fl
     D3fGemm g = in;
     g.partial = nullptr;
     if (g.M <= 0 || g.N <= 0) return D3F_OK;
-    // large-M, N <= 64 problems (KPConv contractions of levels 0-1, their data gradients, the first unary layers):
-    // B-resident mma.sync kernel with a fixed, M-independent summation order, so it also serves the forward pass
-    if (g.K > 0 && d3f_gemm_skinny_eligible(g, ta, tb)) return d3f_gemm_skinny_launch(g, tb, stream);
     const int tiles = d3f_ceil_div(g.M, BM) * d3f_ceil_div(g.N, BN);
     int splits = 1, kps;
     const bool plain = !g.bias && !g.act && !g.bias2 && !g.res;   // atomically combined partials cannot take an epilogue

@@ -31,10 +31,3 @@ struct D3fGemm {
 size_t d3f_gemm_det_workspace_bytes(int M, int N, int K);
 int d3f_gemm_launch(const D3fGemm& g, bool ta, bool tb, cudaStream_t stream, float* det_ws = nullptr,
                     size_t det_ws_bytes = 0);
-
-// skinny-N kernel (gemm_skinny.cu): B resident in shared memory as mma.sync fragments, A streamed from L2 into registers
-#ifndef D3F_GEMM_SKINNY_DEFAULT
-#define D3F_GEMM_SKINNY_DEFAULT 0
-#endif
-bool d3f_gemm_skinny_eligible(const D3fGemm& g, bool ta, bool tb);
-int d3f_gemm_skinny_launch(const D3fGemm& g, bool tb, cudaStream_t stream);

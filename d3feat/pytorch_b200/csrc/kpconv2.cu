@@ -707,10 +707,6 @@ int kp2_correlate_launch(const Kp2Args& a, float* wf, float* wf_unmod, float* in
                : correlate_cg<false, false, 0>(a, HP, grid, warps, smem, wf, wf_unmod, inv_n, min_d2, stream);
 }
 
-// 1 = 128-bit vector reductions for Cin % 128 == 0 (default), 2 = also for Cin = 32 / 64, 0 = always scalar (A/B switch)
-static int g_scatter_vec = 1;
-extern "C" void d3f_set_scatter_vec(int use_vec) { g_scatter_vec = use_vec < 0 ? 1 : (use_vec > 2 ? 2 : use_vec); }
-
 int kp2_scatter_launch(const Kp2Args& a, const float* dwf, const float* wf_unmod, float* grad_x, float* grad_kp,
                        float* grad_mod, cudaStream_t stream) {
     const int HP = kp2_hpad(a.H);
@@ -719,8 +715,8 @@ int kp2_scatter_launch(const Kp2Args& a, const float* dwf, const float* wf_unmod
     const int grid = d3f_ceil_div(a.nq, warps);
     // round 1e micro-benchmark: the reduction rate is per 4-byte element, so the vector form only pays where it also
     // saves shared-memory reads (Cin >= 128: 129 vs 131 us at level 2); at Cin = 32 it is slower (386 vs 300 us)
-    const int vec_min_cin = g_scatter_vec == 2 ? 32 : 128;
-    const bool vec = g_scatter_vec && !a.deformed && grad_x && !grad_kp && !grad_mod && a.cin >= vec_min_cin &&
+    const int vec_min_cin = 128;
+    const bool vec = !a.deformed && grad_x && !grad_kp && !grad_mod && a.cin >= vec_min_cin &&
                      (a.cin == 32 || a.cin == 64 || (a.cin & 127) == 0) && (((size_t)dwf | (size_t)grad_x) & 15) == 0;
     if (vec) return a.idx64 ? scatter_vec<true>(a, HP, grid, warps, smem, dwf, grad_x, stream)
                             : scatter_vec<false>(a, HP, grid, warps, smem, dwf, grad_x, stream);

@@ -21,7 +21,7 @@ import math
 
 import torch
 
-from . import ops
+from . import _lib, ops
 from .blocks import gather
 
 
@@ -181,15 +181,23 @@ class PairStep:
     step = PairStep(model, config, limits, caps, n0, n1, loss_fn, optimizer, flat_grads)
     step.capture()                      # optional: CUDA graph
     loss = step(data)                   # data = (pts0, pts1, feat0, feat1, corr, dist_keypts): tensors on any device
-    step.check()                        # raises if a capacity / candidate buffer overflowed (host sync)
+    step.check()                        # raises if ANY step since the last check overflowed a capacity / candidate
+                                        # buffer, hit a GEMM barrier timeout, or was skipped for a non-finite gradient
+
+    `optimizer`: optim.FlatSGD (the reference's SGD + ExpLR + non-finite guard on flat buffers, gradients written in
+    place, bucketed all-reduce overlapped with backward) or any object with zero_grad() / step() (torch.optim).
     """
+
+    STATUS_EXTRA = 2     # [gemm barrier timeout, step skipped: non-finite gradient] after the pyramid flags
 
     def __init__(self, model, config, limits, caps, n0, n1, loss_fn, optimizer=None, flat_grads=None,
                  num_node=128, group=None, cross_fragment=None):
+        from .optim import FlatSGD, early_block_index
         dev = next(model.parameters()).device
         self.model, self.config, self.limits, self.caps = model, config, [int(v) for v in limits], list(caps)
         self.loss_fn, self.optimizer, self.flat = loss_fn, optimizer, flat_grads
         self.cross_fragment, self.group = cross_fragment, group
+        self.flat_sgd = optimizer if isinstance(optimizer, FlatSGD) else None
         self.n0 = n0
         f32 = dict(dtype=torch.float32, device=dev)
         self.inputs = (torch.zeros((n0, 3), **f32), torch.zeros((n1, 3), **f32), torch.ones((n0, 1), **f32),
@@ -200,15 +208,27 @@ class PairStep:
         self.loss = torch.zeros((), **f32)
         self.desc_loss = torch.zeros((), **f32)
         self.det_loss = torch.zeros((), **f32)
-        self.status = None
+        self.status = None          # sticky: max over every step since the last check()
         self.batch = None
+        self.features = None        # [caps[0], 32] descriptors / [caps[0], 1] scores of the last step (static buffers)
+        self.scores = None
         self.side_stream = torch.cuda.Stream(device=dev)     # grid-subsampling chain
         self.search_stream = torch.cuda.Stream(device=dev)   # radius searches + transposed lists; the network consumes
                                                              # each level as soon as it is ready (see collate_static)
+        if self.flat_sgd is not None and cross_fragment is not None and hasattr(model, "_early_block"):
+            # data parallel: all-reduce the first gradient bucket while the shallow levels still back-propagate
+            model._early_block = early_block_index(model)
+            model._on_early_grads = lambda: self.flat_sgd.allreduce_early(self.group)
 
     # -- the step on the static input buffers
     def _body(self):
+        # without an optimizer the step is forward + loss only: no autograd graph is recorded
+        with torch.set_grad_enabled(self.optimizer is not None):
+            return self._body_impl()
+
+    def _body_impl(self):
         cfg = self.config
+        lib = _lib.load()
         batch, pyramid = collate_static(*self.inputs, cfg, self.limits, self.caps, self.lengths0, self.side_stream,
                                         transposes=self.optimizer is not None, search_stream=self.search_stream)
         feats, scores = self.model(batch)
@@ -222,24 +242,33 @@ class PairStep:
         else:
             out = self.loss_fn(a, p, batch['dist_keypts'], sa, sp)
         loss = out['desc_loss'] * cfg.desc_loss_weight + out['det_loss'] * cfg.det_loss_weight
+        extra = torch.zeros(self.STATUS_EXTRA, dtype=torch.int32, device=status.device)
         if self.optimizer is not None:
             if self.flat is not None:
                 self.flat.zero()
             else:
-                # gradients are (re)created by the backward pass: no zero-fill and no accumulate kernel per parameter
-                # (inside a CUDA graph they come from the graph's private pool at the same addresses every replay)
+                # FlatSGD(direct): every gradient is written in place by the kernel that computes it.  torch.optim:
+                # gradients are (re)created by the backward pass (inside a CUDA graph they come from the graph's private
+                # pool at the same addresses every replay).  Either way: no zero-fill, no accumulate kernel per parameter
                 self.optimizer.zero_grad(set_to_none=True)
             loss.backward()
-            if self.flat is not None:
+            if self.flat_sgd is not None:
+                self.flat_sgd.allreduce(self.group)
+            elif self.flat is not None:
                 self.flat.allreduce(self.group)
-            self.optimizer.step()
+            self.optimizer.step()       # FlatSGD: skipped on the device when a gradient is not finite (trainer.py:104-111)
+            if self.flat_sgd is not None:
+                extra[1:2].copy_(self.flat_sgd.nonfinite)
+        _lib.check(lib.d3f_gemm_status_snapshot(extra.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        status = torch.cat([status, extra])
         self.loss.copy_(loss.detach())
         self.desc_loss.copy_(out['desc_loss'].detach())
         self.det_loss.copy_(out['det_loss'].detach())
         if self.status is None:
             self.status = torch.zeros_like(status)
-        self.status.copy_(status)
+        torch.maximum(self.status, status, out=self.status)      # sticky across steps / graph replays
         self.batch = batch
+        self.features, self.scores = feats.detach(), scores.detach()
         return loss
 
     def load(self, data):
@@ -265,13 +294,20 @@ class PairStep:
         for m in self.model.modules():
             if hasattr(m, "deformed_KP"):
                 m.deformed_KP = m.offset_features = m.min_d2 = None
-        self.batch = None
+        self.batch = self.features = self.scores = None
         gc.collect()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._body()
         self.graph = g
         return self
+
+    def release(self):
+        """Drop the captured graph (and the NCCL kernels it holds) -- call before destroying the process group."""
+        self.graph = None
+        self.batch = self.features = self.scores = None
+        if hasattr(self.model, "_on_early_grads"):
+            self.model._on_early_grads = None
 
     def __call__(self, data=None):
         if data is not None:
@@ -282,9 +318,24 @@ class PairStep:
             self._body()
         return self.loss
 
-    def check(self):
-        """Host-side validity check of the last step (one small D2H read)."""
-        if self.status is not None and bool(self.status.any()):
-            raise RuntimeError("PairStep: a static capacity or a neighbour candidate buffer overflowed "
-                               "(status=%s); re-plan the capacities or use the exact-shape pipeline"
-                               % self.status.tolist())
+    def check(self, allow_skipped=False):
+        """Host-side validity check of EVERY step since the previous check (one small D2H read; clears the flags).
+        allow_skipped: a step skipped by the non-finite-gradient guard is what the reference does silently
+        (trainer.py:104-111); a benchmark must not tolerate it (skipped work), a training loop may."""
+        if self.status is None:
+            return
+        st = self.status.tolist()
+        self.status.zero_()
+        if allow_skipped:
+            st[-1] = 0
+        if any(st):
+            pyr, (gemm_to, skipped) = st[:-self.STATUS_EXTRA], st[-self.STATUS_EXTRA:]
+            what = []
+            if any(pyr):
+                what.append("a static capacity or a neighbour candidate buffer overflowed (pyramid flags %s); re-plan the "
+                            "capacities or use the exact-shape pipeline" % pyr)
+            if gemm_to:
+                what.append("a tcgen05 GEMM timed out on its mbarrier (output tile NaN-poisoned)")
+            if skipped:
+                what.append("an optimizer step was skipped: non-finite gradient (trainer.py:104-111 semantics)")
+            raise RuntimeError("PairStep: " + "; ".join(what))

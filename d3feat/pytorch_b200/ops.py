@@ -225,7 +225,7 @@ def neighbors_transpose(inds, n_supports):
 
 
 def kpconv_backward(q_pts, s_pts, inds, x, weights, kernel_points, extent, influence, aggregation, deformed,
-                    modulations, wf, wf_un, inv_n, grad_out, need_x, need_w, need_kp, need_mod, transpose=None):
+                    modulations, wf, wf_un, inv_n, grad_out, need_x, need_w, need_kp, need_mod, transpose=None, gw_out=None):
     """d3f_kpconv_backward_ex.  `transpose` = (t_offsets, t_src) from neighbors_transpose selects the atomic-free
     grad_x where the layer allows it (rigid, Cout % 32 == 0)."""
     lib = _lib.load()
@@ -234,7 +234,7 @@ def kpconv_backward(q_pts, s_pts, inds, x, weights, kernel_points, extent, influ
     K, cin, cout = weights.shape
     grad_out = _cuda_f32(grad_out, "grad_out")
     gx = torch.empty((ns, cin), dtype=torch.float32, device=dev) if need_x else None
-    gw = torch.empty_like(weights) if need_w else None
+    gw = (gw_out if gw_out is not None else torch.empty_like(weights)) if need_w else None
     gkp = torch.empty((nq, K, 3), dtype=torch.float32, device=dev) if (need_kp and deformed) else None
     gmod = torch.empty((nq, K), dtype=torch.float32, device=dev) if (need_mod and modulations is not None) else None
     ws = _ws(lib.d3f_kpconv_workspace_bytes(nq, ns, H, K, cin, cout), dev)
@@ -460,8 +460,14 @@ def detection_scores(feats, neighbors, eval_mode):
 
 
 # --------------------------------------------------------------------------- tensor-core GEMM (3xTF32) + fused linear
+def grad_dst(param):
+    """Destination a backward kernel writes the gradient of `param` into (optim.FlatSGD(direct=True) attaches a view of
+    its flat gradient buffer), or None: the gradient is then returned to autograd as usual."""
+    return getattr(param, "_d3f_grad", None) if param is not None else None
+
+
 def gemm(a, b, trans_a=False, trans_b=False, row_scale=None, k_scale=None, bias=None, slope=None, deterministic=False,
-         bias2=None, residual=None):
+         bias2=None, residual=None, out=None):
     """C = act(row_scale * opA(a) @ (k_scale * opB(b)) + bias + bias2 + residual) via d3f_gemm / d3f_gemm_ex
     (fp32-accurate tensor-core GEMM).  a: [M,K] (or [K,M] if trans_a); b: [K,N] (or [N,K] if trans_b).
     deterministic=True (forward pass): d3f_gemm_ex, whose split-K depends on K only and sums its partials in a fixed
@@ -473,7 +479,12 @@ def gemm(a, b, trans_a=False, trans_b=False, row_scale=None, k_scale=None, bias=
     kb = b.shape[1] if trans_b else b.shape[0]
     if kb != K:
         raise RuntimeError("gemm: inner dimensions differ (%d vs %d)" % (K, kb))
-    c = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    if out is not None:
+        if out.numel() != M * N or out.dtype != torch.float32 or not out.is_contiguous():
+            raise RuntimeError("gemm: `out` must be a contiguous fp32 tensor of %d elements" % (M * N))
+        c = out
+    else:
+        c = torch.empty((M, N), dtype=torch.float32, device=a.device)
     global launch_count
     launch_count += 1
     head = (int(trans_a), int(trans_b), M, N, K, _p(a), a.stride(0), _p(b), b.stride(0), _p(c), N,
@@ -495,11 +506,12 @@ def gemm(a, b, trans_a=False, trans_b=False, row_scale=None, k_scale=None, bias=
     return c
 
 
-def colsum(x):
+def colsum(x, out=None):
     """x.sum(dim=0) for a 2-D fp32 CUDA tensor (d3f_colsum)."""
     lib = _lib.load()
     x = _cuda_f32(x, "x")
-    out = torch.empty(x.shape[1], dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty(x.shape[1], dtype=torch.float32, device=x.device)
     _lib.check(lib.d3f_colsum(_p(x), x.shape[0], x.shape[1], _p(out), _stream()))
     return out
 
@@ -535,7 +547,7 @@ def run_branches(side_fn, main_fn, device):
     return a, b
 
 
-def leaky_backward_colsum(gy, y, slope, want_colsum=True):
+def leaky_backward_colsum(gy, y, slope, want_colsum=True, db_out=None):
     """(dz, colsum(dz)) with dz = gy * (y > 0 ? 1 : slope), y = the saved LeakyReLU output: one kernel
     (d3f_leaky_backward_colsum) where the channel count allows it, else ATen's leaky_relu_backward + d3f_colsum."""
     lib = _lib.load()
@@ -543,14 +555,14 @@ def leaky_backward_colsum(gy, y, slope, want_colsum=True):
     M, N = gy.shape
     if want_colsum:
         dz = torch.empty_like(gy)
-        db = torch.empty(N, dtype=torch.float32, device=gy.device)
+        db = db_out if db_out is not None else torch.empty(N, dtype=torch.float32, device=gy.device)
         rc = lib.d3f_leaky_backward_colsum(_p(gy), _p(y), float(slope), M, N, _p(dz), _p(db), _stream())
         if rc == 0:
             return dz, db
         if rc != -4:   # D3F_ERR_UNSUPPORTED: shape not covered by the vector kernel
             _lib.check(rc)
     dz = torch.ops.aten.leaky_relu_backward(gy, y, float(slope), True).contiguous()
-    return dz, (colsum(dz) if want_colsum else None)
+    return dz, (colsum(dz, out=db_out) if want_colsum else None)
 
 
 class _FusedLinear(torch.autograd.Function):
@@ -559,30 +571,48 @@ class _FusedLinear(torch.autograd.Function):
     tail of ResnetBottleneckBlock (leaky_relu(unary2(x) + shortcut), blocks.py:686) as ONE GEMM with a fused epilogue."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, bias2, residual, slope):
+    def forward(ctx, x, weight, bias, bias2, residual, slope, dsts):
         y = gemm(x, weight, trans_b=True, bias=bias, slope=slope, deterministic=True, bias2=bias2, residual=residual)
         ctx.save_for_backward(x, weight, y if slope is not None else None)
         ctx.slope = slope
+        ctx.dsts = dsts      # (dW, db, db2) destinations inside a flat gradient buffer, or Nones
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, weight, y = ctx.saved_tensors
         need = ctx.needs_input_grad
+        dst_w, dst_b, dst_b2 = ctx.dsts
         want_db = need[2] or need[3]
+        db_out = dst_b if (need[2] and dst_b is not None) else (dst_b2 if (need[3] and dst_b2 is not None) else None)
         if y is None:
             dz = gy.contiguous()
-            db = colsum(dz) if want_db else None
+            db = colsum(dz, out=db_out) if want_db else None
         else:   # y = leaky(z) has the sign of z (slope > 0): the mask comes from the saved output, fused with the bias grad
-            dz, db = leaky_backward_colsum(gy, y, ctx.slope, want_db)
+            dz, db = leaky_backward_colsum(gy, y, ctx.slope, want_db, db_out)
         if need[0] and need[1]:
-            dw, dx = run_branches(lambda: gemm(dz, x, trans_a=True),    # dz^T [out,M] @ x [M,in]
-                                  lambda: gemm(dz, weight), dz.device)  # [M,out] @ [out,in]
+            dw, dx = run_branches(lambda: gemm(dz, x, trans_a=True, out=dst_w),    # dz^T [out,M] @ x [M,in]
+                                  lambda: gemm(dz, weight), dz.device)             # [M,out] @ [out,in]
         else:
             dx = gemm(dz, weight) if need[0] else None
-            dw = gemm(dz, x, trans_a=True) if need[1] else None
-        return dx, dw, db if need[2] else None, db if need[3] else None, dz if need[4] else None, None
+            dw = gemm(dz, x, trans_a=True, out=dst_w) if need[1] else None
+        gb = gb2 = None
+        if want_db:
+            if db_out is None:                      # plain autograd gradients
+                gb, gb2 = (db if need[2] else None), (db if need[3] else None)
+            elif db_out is dst_b:                   # written in place; the second bias gets the same column sums
+                if need[3]:
+                    if dst_b2 is not None:
+                        dst_b2.copy_(db)
+                    else:
+                        gb2 = db.clone()
+            else:                                   # db_out is dst_b2
+                if need[2]:
+                    gb = db.clone()
+        if dst_w is not None:
+            dw = None
+        return dx, dw, gb, gb2, dz if need[4] else None, None, None
 
 
 def fused_linear(x, weight, bias, slope=None, bias2=None, residual=None):
-    return _FusedLinear.apply(x, weight, bias, bias2, residual, slope)
+    return _FusedLinear.apply(x, weight, bias, bias2, residual, slope, (grad_dst(weight), grad_dst(bias), grad_dst(bias2)))

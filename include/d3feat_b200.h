@@ -10,7 +10,9 @@
  *   - all matrices are dense row-major; indices are int32 or int64 as flagged;
  *   - return value: D3F_OK (0) or a negative d3f_status; d3f_last_error_string()
  *     describes the last failure on the calling thread;
- *   - thread-safe for calls that use distinct streams and distinct buffers.
+ *   - thread-safe for calls that use distinct streams and distinct buffers: nothing in this header reads or writes
+ *     process-global state (the A/B selectors and measurement hooks of the test suite live in d3feat_b200_debug.h
+ *     and are not part of the product ABI).
  *
  * Each entry point cites the reference interface it replaces (file:line under the
  * XuyangBai/D3Feat.pytorch tree).  INTEGRATION.md shows the reference-side binding.
@@ -131,19 +133,6 @@ int d3f_kpconv_forward_ex(const float* q_pts, const float* s_pts, const void* in
                           const float* bias, int leaky_relu, float slope,
                           float* out, float* wf, float* wf_unmod, float* inv_n, float* min_d2,
                           void* workspace, size_t workspace_bytes, d3f_stream stream);
-
-/* Gather-kernel generation used by d3f_kpconv_forward/_backward: 0 = v1 (warp per query, lanes over neighbours),
- * 1 = v2 with FFMA accumulation, 2 = v2 with mma.sync 3xTF32 accumulation (csrc/kpconv2.cu); -1 restores the default
- * (environment D3F_KPCONV_IMPL = v1 | ffma | mma, else 2).  All three compute the same function; the selector
- * exists for A/B measurements and parity tests. */
-void d3f_set_kpconv_impl(int impl);
-int d3f_get_kpconv_impl(void);
-/* v2 backward scatter (the path without transposed lists): 1 = 128-bit vector reductions (red.global.add.v4.f32) for
- * Cin % 128 == 0 (default), 2 = also for Cin = 32 / 64, 0 = scalar reductions only. */
-void d3f_set_scatter_vec(int use_vec);
-/* Measurement hook: cudaEvent_t handles (or NULL, NULL) recorded on the caller's stream right before and right after
- * the forward gather kernel of the next d3f_kpconv_forward calls, so that kernel can be timed alone. */
-void d3f_kpconv_set_gather_events(void* start_event, void* stop_event);
 
 /* backward: grad_out [Nq,Cout] ->
  *   grad_x [Ns,Cin] or NULL (fully overwritten), grad_weights [K,Cin,Cout] or NULL (overwritten),
@@ -274,19 +263,6 @@ int d3f_mutual_nn(const float* source, const float* target, int n_source, int n_
  *   trans_a: A stored [K,M] else [M,K];  trans_b: B stored [N,K] else [K,N]  (row-major, lda/ldb/ldc in elements)
  *   row_scale / k_scale / bias may be NULL; k_scale needs trans_b == 0; leaky_relu != 0 applies max(v, slope*v).
  */
-/* GEMM back end: 1 = tcgen05.mma + TMEM (default), 0 = legacy mma.sync; d3f_gemm_tcgen05_failed() returns 1 if a
- * tcgen05 kernel ever gave up waiting on its mbarrier (diagnostic, synchronises the device). */
-void d3f_set_gemm_impl(int use_tcgen05);
-/* tcgen05 back end only, kernel variant: 0 = register-fed, one operand stage, 3-4 CTAs/SM (default); 1 = A operand
- * through a cp.async ring (needs a 16-byte aligned A); 2 = warp-specialised (8 converter warps + 1 MMA warp, two
- * operand stages); 3 = EXPERIMENTAL (numerically validated, not yet timed): A operand in tensor memory (tcgen05.st + TMEM-A MMA);
- * -1 = default (environment D3F_GEMM_PIPELINE = reg | cpasync | ws | tmem, else the library's built-in choice). */
-void d3f_set_gemm_pipeline(int variant);
-/* B-resident mma.sync kernel (csrc/gemm_skinny.cu) for N <= 64, K % 16 == 0, non-transposed-A problems: 2 = every such
- * problem with M >= 2048, 1 = only large-M problems whose B fits one resident chunk, 0 = never,
- * -1 = default (environment D3F_GEMM_SKINNY = 0 | 1 | 2, else the library's built-in choice). */
-void d3f_set_gemm_skinny(int on);
-int d3f_gemm_tcgen05_failed(void);
 int d3f_gemm(int trans_a, int trans_b, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
              float* C, int ldc, const float* row_scale, const float* k_scale, const float* bias,
              int leaky_relu, float slope, d3f_stream stream);
@@ -301,6 +277,22 @@ int d3f_gemm_ex(int trans_a, int trans_b, int M, int N, int K, const float* A, i
                 float* C, int ldc, const float* row_scale, const float* k_scale, const float* bias,
                 const float* bias2, const float* residual, int ld_residual,
                 int leaky_relu, float slope, void* workspace, size_t workspace_bytes, d3f_stream stream);
+
+/* out[0] (device int32) = 1 if a tcgen05 GEMM of this process ever gave up waiting on its mbarrier (the affected output
+ * tile is NaN-poisoned); asynchronous device-to-device copy on `stream`, usable inside a CUDA-graph capture. */
+int d3f_gemm_status_snapshot(int32_t* out, d3f_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimiser step on flat buffers.  Replaces torch.optim.SGD.step() as configured by
+ * training_3DMatch.py:62-69 (momentum, weight decay, dampening 0) guarded by the reference trainer's
+ * "skip the step when a gradient is not finite" loop (trainer.py:104-111), without a host round trip:
+ *   g' = g + weight_decay * p;  m = momentum * m + g';  p -= lr[0] * m       (params, momentum_buf updated in place)
+ *   params, grads, momentum_buf: n fp32 elements each, 16-byte aligned;  lr: device float (ExponentialLR multiplies it
+ *   between epochs, training_3DMatch.py:77-80);  nonfinite_flag: device int32, OR-ed with 1 when check_finite != 0 and
+ *   some gradient element is inf / nan; when the flag is non-zero the update is skipped.  The caller clears the flag.
+ */
+int d3f_sgd_step(float* params, const float* grads, float* momentum_buf, size_t n, const float* lr,
+                 float momentum, float weight_decay, int32_t* nonfinite_flag, int check_finite, d3f_stream stream);
 
 #ifdef __cplusplus
 }

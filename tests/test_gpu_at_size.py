@@ -1,0 +1,318 @@
+"""Parity AT THE SIZES THE BENCHMARK TIMES: BASELINE.json configs 2, 3 (20k+20k points,
+default width 128) and 4 (deformable blocks, 40k+40k points), the (B*P)^2 cross-fragment loss at P = 1024 with +inf
+off-block keypoint distances, and -- with two GPUs -- the NCCL exchange itself.
+
+Index bar: bit-exact against the reference C++ (oracle/_ref when present, else its plain-C port).  Float bar: 1e-4
+relative (BASELINE.json north_star), written in each test."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+import _inputs
+from _util import rel_err
+from d3feat.pytorch_b200 import synthetic
+from d3feat.pytorch_b200.config import build_architecture, default_config
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _impl(oracle_cpu):
+    return "ref" if os.path.exists(os.path.join(os.path.dirname(oracle_cpu.__file__), "_ref", "libd3feat_ref.so")) else "port"
+
+
+def _limits(n, deform):
+    if n == 20000 and not deform:
+        return [35, 42, 42, 45, 47]       # 80th-percentile rule on these pairs (bench.py CONFIGS)
+    return None
+
+
+def _cpu_reference(data, cfg, limits, sd, impl, backward):
+    from oracle import model_ref, pipeline
+    cpu_b = pipeline.cpu_collate(data, cfg, limits, impl=impl)
+    params = {k: v.clone().requires_grad_(backward and "kernel_points" not in k) for k, v in sd.items()}
+    with torch.set_grad_enabled(backward):
+        f, s = model_ref.kpfcnn_forward(params, cpu_b, cfg, training=True)
+        dl, det, _, _ = model_ref.pair_losses(f, s, cpu_b, "circle")
+        if backward:
+            (dl + det).backward()
+    grads = {k: p.grad for k, p in params.items() if p.grad is not None}
+    return cpu_b, f.detach(), s.detach(), dl.detach(), det.detach(), grads
+
+
+def _assert_pyramid_equal(batch, cpu_b):
+    n_cmp = 0
+    for l in range(len(cpu_b["points"])):
+        assert np.array_equal(batch["points"][l].cpu().numpy().view(np.uint32), cpu_b["points"][l].numpy().view(np.uint32)), \
+            "points level %d" % l
+        assert batch["stack_lengths"][l].tolist() == cpu_b["stack_lengths"][l].tolist()
+        for key in ("neighbors", "pools", "upsamples"):
+            e = cpu_b[key][l]
+            if e.numel() == 0:
+                continue
+            assert torch.equal(batch[key][l].cpu().long(), e), "%s level %d" % (key, l)
+            n_cmp += e.numel()
+    return n_cmp
+
+
+@pytest.mark.parametrize("name,n,deform", [("config2/3: 20k+20k rigid, width 128", 20000, False),
+                                           ("config4: 40k+40k deformable levels 3-4", 40000, True)])
+def test_pair_at_baseline_size_vs_oracle(cuda, oracle_cpu, name, n, deform):
+    """All 13 radius searches + 4 grid subsamplings bit-exact; descriptors, scores, circle + detector loss within 1e-4;
+    gradients of the flip-free head at 1e-4 and every other tensor inside the ReLU-flip envelope (flip-sized outliers
+    are counted and printed)."""
+    from d3feat.pytorch_b200.architectures import KPFCNN
+    from d3feat.pytorch_b200.blocks import gather
+    from d3feat.pytorch_b200.dataloader import calibrate_neighbors, collate_fn_descriptor
+    from d3feat.pytorch_b200.loss import PairLoss
+    kw = dict(architecture=build_architecture(5, deformable_from=3)) if deform else {}
+    cfg = default_config(**kw)                      # first_features_dim = 128: the width bench.py times
+    data = synthetic.fragment_pair(n, seed=0)
+    limits = _limits(n, deform)
+    if limits is None:
+        class DS:
+            config = cfg
+            def __len__(self): return 1
+            def __getitem__(self, i): return data
+        limits = [int(v) for v in calibrate_neighbors(DS(), cfg, collate_fn_descriptor, samples_threshold=10 ** 9)]
+    sd = _inputs.kpfcnn_state_dict(cfg, seed=0)
+    impl = _impl(oracle_cpu)
+    cpu_b, f_ref, s_ref, dl_ref, det_ref, g_ref = _cpu_reference(data, cfg, limits, sd, impl, backward=True)
+
+    batch = collate_fn_descriptor([data], cfg, limits)
+    n_idx = _assert_pyramid_equal(batch, cpu_b)
+    model = KPFCNN(cfg).to(cuda)
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    feats, scores = model(batch)
+    c = batch["corr"].long()
+    ia, ip = c[:, 0], c[:, 1] + n
+    o = PairLoss("circle", "euclidean", 10, 0.1, 0.1, 1.4)(gather(feats, ia), gather(feats, ip), batch["dist_keypts"],
+                                                          gather(scores, ia), gather(scores, ip))
+    (o["desc_loss"] + o["det_loss"]).backward()
+    errs = dict(features=rel_err(feats.detach().cpu(), f_ref), scores=rel_err(scores.detach().cpu(), s_ref),
+                desc=rel_err(o["desc_loss"].detach().cpu(), dl_ref), det=rel_err(o["det_loss"].detach().cpu(), det_ref))
+    gerr = {k: rel_err(p.grad.cpu(), g_ref[k]) for k, p in model.named_parameters() if p.grad is not None}
+    head = [k for k in gerr if k.startswith("decoder_blocks.%d." % (len(model.decoder_blocks) - 1))]
+    outliers = sorted(k for k, v in gerr.items() if v >= TOL)
+    print(name, "| limits", limits, "| %d indices bit-exact (%s) |" % (n_idx, impl), {k: "%.1e" % v for k, v in errs.items()},
+          "| grads: head %s, median %.1e, max %.1e, tensors >= 1e-4: %d of %d"
+          % ({k.split(".", 2)[2]: "%.1e" % gerr[k] for k in head}, float(np.median(list(gerr.values()))),
+             max(gerr.values()), len(outliers), len(gerr)))
+    assert max(errs.values()) < TOL, errs
+    assert head and all(gerr[k] < TOL for k in head), {k: gerr[k] for k in head}
+    # LeakyReLU / max-pool / in-range-filter flips (see test_gpu_model.py): bounded envelope, bulk at 1e-4
+    assert float(np.median(list(gerr.values()))) < TOL and max(gerr.values()) < 0.3, outliers
+
+
+def test_static_graph_step_at_20k_matches_oracle(cuda, oracle_cpu):
+    """What bench.py replays: engine.PairStep (static capacities, one CUDA graph, FlatSGD) on a 20k+20k pair --
+    indices of the capacity-padded pyramid, descriptors, scores and both losses against the CPU oracle."""
+    from d3feat.pytorch_b200.architectures import KPFCNN
+    from d3feat.pytorch_b200.dataloader import collate_fn_descriptor
+    from d3feat.pytorch_b200.engine import PairStep, plan_capacities
+    from d3feat.pytorch_b200.loss import PairLoss
+    from d3feat.pytorch_b200.optim import FlatSGD
+    n, cfg, limits = 20000, default_config(), [35, 42, 42, 45, 47]
+    data = synthetic.fragment_pair(n, seed=1)
+    sd = _inputs.kpfcnn_state_dict(cfg, seed=0)
+    cpu_b, f_ref, s_ref, dl_ref, det_ref, _ = _cpu_reference(data, cfg, limits, sd, _impl(oracle_cpu), backward=False)
+    model = KPFCNN(cfg).to(cuda)
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    opt = FlatSGD(model, lr=0.0)                    # lr 0: replays leave the weights where the oracle has them
+    sizes = [int(p.shape[0]) for p in collate_fn_descriptor([data], cfg, limits)["points"]]
+    caps = plan_capacities([sizes])
+    st = PairStep(model, cfg, limits, caps, n, n, PairLoss("circle", "euclidean", 10, 0.1, 0.1, 1.4), opt, None)
+    opt.verify_direct(lambda: st(data))
+    st.capture()
+    st(data); st(data)
+    torch.cuda.synchronize()
+    st.check()
+    for l, nl in enumerate(sizes):
+        assert torch.equal(st.batch["points"][l][:nl].cpu(), cpu_b["points"][l])
+        for key in ("neighbors", "pools", "upsamples"):
+            e = cpu_b[key][l]
+            if e.numel() == 0:
+                continue
+            n_sup, cap_sup = (sizes[l + 1], caps[l + 1]) if key == "upsamples" else (sizes[l], caps[l])
+            got = st.batch[key][l][:e.shape[0], :e.shape[1]].long().cpu()
+            assert torch.equal(got, torch.where(e == n_sup, torch.full_like(e, cap_sup), e)), (key, l)
+    errs = dict(features=rel_err(st.features[:2 * n].cpu(), f_ref), scores=rel_err(st.scores[:2 * n].cpu(), s_ref),
+                desc=rel_err(st.desc_loss.cpu(), dl_ref), det=rel_err(st.det_loss.cpu(), det_ref))
+    print("graph step @20k:", {k: "%.1e" % v for k, v in errs.items()})
+    assert max(errs.values()) < TOL, errs
+    st.release()
+
+
+@pytest.mark.parametrize("world,P", [(8, 128), (2, 128), (1, 1024)])
+def test_pair_loss_cross_fragment_size_with_inf_offblock(cuda, world, P):
+    """PairLoss at B*P = 1024 with dist_keypts = +inf off the block diagonal (what SCALE N = 8 evaluates), forward and
+    gradients, against the oracle's CircleLoss + DetLoss on the concatenated batch."""
+    from oracle import model_ref
+    from d3feat.pytorch_b200.loss import PairLoss
+    rng = np.random.default_rng(world * 1000 + P)
+    n = world * P
+    a = rng.standard_normal((n, 32)); a /= np.linalg.norm(a, axis=1, keepdims=True)
+    p = a + 0.35 * rng.standard_normal((n, 32)); p /= np.linalg.norm(p, axis=1, keepdims=True)
+    kp = rng.random((n, 3)) * 1.5
+    dk = np.full((n, n), np.inf)
+    for r in range(world):
+        blk = kp[r * P:(r + 1) * P]
+        dk[r * P:(r + 1) * P, r * P:(r + 1) * P] = np.sqrt(((blk[:, None] - blk[None]) ** 2).sum(-1))
+    sa, sp = rng.random((n, 1)) + 0.1, rng.random((n, 1)) + 0.1
+    t = lambda v, d=None: torch.from_numpy(np.asarray(v, np.float32))  # noqa: E731
+    ca, cp, csa, csp = (t(a).requires_grad_(True), t(p).requires_grad_(True), t(sa).requires_grad_(True), t(sp).requires_grad_(True))
+    dl, _, _, _, d = model_ref.circle_loss(ca, cp, torch.from_numpy(dk))
+    det = model_ref.det_loss(d, csa, csp)
+    (dl + det).backward()
+    ga, gp, gsa, gsp = (t(a).to(cuda).requires_grad_(True), t(p).to(cuda).requires_grad_(True),
+                        t(sa).to(cuda).requires_grad_(True), t(sp).to(cuda).requires_grad_(True))
+    o = PairLoss("circle", "euclidean", 10, 0.1, 0.1, 1.4)(ga, gp, torch.from_numpy(dk).to(cuda), gsa, gsp)
+    (o["desc_loss"] + o["det_loss"]).backward()
+    errs = dict(desc=rel_err(o["desc_loss"].detach().cpu(), dl.detach()), det=rel_err(o["det_loss"].detach().cpu(), det.detach()),
+                dA=rel_err(ga.grad.cpu(), ca.grad), dB=rel_err(gp.grad.cpu(), cp.grad),
+                dSa=rel_err(gsa.grad.cpu(), csa.grad), dSp=rel_err(gsp.grad.cpu(), csp.grad))
+    print("PairLoss %d x %d (world %d):" % (n, n, world), {k: "%.1e" % v for k, v in errs.items()})
+    assert max(errs.values()) < TOL, errs
+
+
+# ------------------------------------------------------------------------------------------- NCCL (needs >= 2 GPUs)
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _xfrag_inputs(rank, P=128, D=32):
+    rng = np.random.default_rng(500 + rank)
+    a = rng.standard_normal((P, D)); a /= np.linalg.norm(a, axis=1, keepdims=True)
+    p = a + 0.35 * rng.standard_normal((P, D)); p /= np.linalg.norm(p, axis=1, keepdims=True)
+    kp = rng.random((P, 3)) * 1.5
+    dk = np.sqrt(((kp[:, None] - kp[None]) ** 2).sum(-1))
+    return (torch.from_numpy(a.astype(np.float32)), torch.from_numpy(p.astype(np.float32)),
+            torch.from_numpy((rng.random((P, 1)) + 0.1).astype(np.float32)),
+            torch.from_numpy((rng.random((P, 1)) + 0.1).astype(np.float32)), torch.from_numpy(dk))
+
+
+def _nccl_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from d3feat.pytorch_b200 import parallel
+    from d3feat.pytorch_b200.loss import PairLoss
+    a, p, sa, sp, dk = (t.to(dev) for t in _xfrag_inputs(rank))
+    for t in (a, p, sa, sp):
+        t.requires_grad_(True)
+    o = parallel.cross_fragment_loss(PairLoss("circle", "euclidean", 10, 0.1, 0.1, 1.4), a, p, dk, sa, sp)
+    (o["desc_loss"] + o["det_loss"]).backward()
+    out[rank] = dict(desc=float(o["desc_loss"]), det=float(o["det_loss"]), ga=a.grad.cpu(), gp=p.grad.cpu(),
+                     gsa=sa.grad.cpu(), gsp=sp.grad.cpu())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_cross_fragment_loss_nccl_two_ranks(cuda):
+    """parallel.cross_fragment_loss over NCCL on 2 GPUs (packed all-gather, PairLoss kernel at 2P x 2P, local-slice
+    gradients) against the oracle's loss on the concatenated batch."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under `gpurun --gpus 2`)")
+    import torch.multiprocessing as mp
+    from oracle import model_ref
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_nccl_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    parts = [_xfrag_inputs(r) for r in range(world)]
+    A, Pos, SA, SP = (torch.cat([x[i] for x in parts]).requires_grad_(True) for i in range(4))
+    P = parts[0][0].shape[0]
+    DK = torch.full((world * P, world * P), float("inf"), dtype=torch.float64)
+    for r in range(world):
+        DK[r * P:(r + 1) * P, r * P:(r + 1) * P] = parts[r][4]
+    dl, _, _, _, d = model_ref.circle_loss(A, Pos, DK)
+    det = model_ref.det_loss(d, SA, SP)
+    (dl + det).backward()
+    for r in range(world):
+        sl = slice(r * P, (r + 1) * P)
+        errs = dict(desc=abs(out[r]["desc"] - float(dl)) / abs(float(dl)), det=abs(out[r]["det"] - float(det)) / abs(float(det)),
+                    dA=rel_err(out[r]["ga"], A.grad[sl]), dB=rel_err(out[r]["gp"], Pos.grad[sl]),
+                    dSa=rel_err(out[r]["gsa"], SA.grad[sl]), dSp=rel_err(out[r]["gsp"], SP.grad[sl]))
+        print("rank", r, {k: "%.1e" % v for k, v in errs.items()})
+        assert max(errs.values()) < TOL, errs
+
+
+# ------------------------------------------------------------------------------------------- optimiser (row f4)
+def test_three_graph_steps_reproduce_three_oracle_sgd_steps(cuda, oracle_cpu):
+    """3 replays of the captured step (pyramid + fwd + loss + bwd + FlatSGD) == 3 oracle cpu_pair_step(sgd=...) steps:
+    losses at 1e-4, final weights at 1e-4 of their update, plus the ExpLR device scalar and the non-finite guard."""
+    from oracle import pipeline
+    from d3feat.pytorch_b200.architectures import KPFCNN
+    from d3feat.pytorch_b200.dataloader import collate_fn_descriptor
+    from d3feat.pytorch_b200.engine import PairStep, plan_capacities
+    from d3feat.pytorch_b200.loss import PairLoss
+    from d3feat.pytorch_b200.optim import FlatSGD
+    n, limits = 1500, [40, 40, 40, 40, 40]
+    cfg = default_config(first_features_dim=32, num_node=64)
+    pairs = [synthetic.fragment_pair(n, seed=40 + i, num_node=64) for i in range(3)]
+    sd0 = _inputs.kpfcnn_state_dict(cfg, seed=3)
+    sd, sgd, ref_losses = {k: v.clone() for k, v in sd0.items()}, {}, []
+    for d in pairs:
+        _, lv = pipeline.cpu_pair_step(d, sd, cfg, limits, impl="port", backward=True, sgd=sgd)
+        ref_losses.append(lv)
+    model = KPFCNN(cfg).to(cuda)
+    model.load_state_dict(sd0, strict=True)
+    model.train()
+    opt = FlatSGD(model, lr=0.01, momentum=0.98, weight_decay=1e-6)
+    sizes = [[int(p.shape[0]) for p in collate_fn_descriptor([d], cfg, limits)["points"]] for d in pairs]
+    st = PairStep(model, cfg, limits, plan_capacities(sizes, margin=1.2, align=32), n, n,
+                  PairLoss("circle", "euclidean", 10, 0.1, 0.1, 1.4), opt, None, num_node=64)
+    # capture BEFORE any real step (warm-up steps would move the weights): lr 0 during warm-up and capture
+    opt.lr.zero_()
+    opt.verify_direct(lambda: st(pairs[0]))
+    st.capture()
+    opt.flat_m.zero_()
+    opt.lr.fill_(0.01)
+    got = []
+    for d in pairs:
+        st(d)
+        got.append(float(st.loss))
+    st.check()
+    print("losses gpu", got, "oracle", ref_losses)
+    for a, b in zip(got, ref_losses):
+        assert abs(a - b) < TOL * max(1.0, abs(b))
+    # weights moved by 3 SGD steps: compare the UPDATE (w - w0), which is what the optimiser computes
+    upd_err = []
+    for k, p in model.named_parameters():
+        du_ref = (sd[k] - sd0[k]).double()
+        du = (p.detach().cpu() - sd0[k]).double()
+        if float(du_ref.abs().max()) > 0:
+            upd_err.append(float((du - du_ref).abs().max() / du_ref.abs().max()))
+    print("update rel err: median %.1e max %.1e" % (float(np.median(upd_err)), max(upd_err)))
+    assert float(np.median(upd_err)) < TOL and max(upd_err) < 0.3       # flip envelope as in test_gpu_model.py
+    # ExpLR: the captured graph reads the new rate from device memory
+    opt.scheduler_step()
+    assert abs(float(opt.lr) - 0.01 * 0.1 ** (1 / 80)) < 1e-9
+    # non-finite guard: an inf in the head's bias makes every gradient NaN -> the step is skipped on the device and flagged
+    head_bias = model.decoder_blocks[-1].mlp.bias
+    keep = float(head_bias[0])
+    head_bias.data[0] = float("inf")
+    before = opt.flat_p.clone()
+    st(pairs[0])
+    torch.cuda.synchronize()
+    assert int(opt.nonfinite) == 1 and torch.equal(opt.flat_p.nan_to_num(), before.nan_to_num())
+    assert torch.equal(torch.isfinite(opt.flat_p), torch.isfinite(before))
+    with pytest.raises(RuntimeError, match="skipped"):
+        st.check()
+    head_bias.data[0] = keep
+    before = opt.flat_p.clone()
+    st(pairs[1])
+    st.check()
+    assert int(opt.nonfinite) == 0 and not torch.equal(opt.flat_p, before)
+    st.release()

@@ -8,29 +8,17 @@ from _util import rel_err
 pytestmark = pytest.mark.gpu
 
 
-import os
-
-# the A-operand-in-tensor-memory variant (tc8) was written at the very end of round 1: its fp64-parity cases passed on a
-# B200 (profiles/r1q_tc8_parity.log) but the rest of the suite has not run on it, so it stays opt-in
-# (D3F_TEST_EXPERIMENTAL=1) until round 2 has timed it
-_GEMM_IMPLS = ["tcgen05-reg", "tcgen05-cpasync", "tcgen05-ws", "mma"] + (
-    ["tcgen05-tmem"] if os.environ.get("D3F_TEST_EXPERIMENTAL") == "1" else [])
-
-
-@pytest.fixture(params=_GEMM_IMPLS)
+@pytest.fixture(params=["tcgen05", "mma"])
 def gemm_impl(request, cuda):
-    """tcgen05-reg = register-fed one-stage kernel, tcgen05-cpasync = A through a cp.async ring (where A is 16-byte
-    aligned), tcgen05-ws = warp-specialised two-stage kernel, tcgen05-tmem = A operand in tensor memory (experimental),
-    mma = legacy mma.sync kernel."""
+    """tcgen05 = the product kernel (tcgen05.mma, accumulators in TMEM); mma = legacy mma.sync kernel (debug selector,
+    include/d3feat_b200_debug.h).  Round 2 deleted the cp.async / warp-specialised / TMEM-A variants after timing them."""
     from d3feat.pytorch_b200 import _lib
     lib = _lib.load()
     lib.d3f_set_gemm_impl(0 if request.param == "mma" else 1)
-    lib.d3f_set_gemm_pipeline({"tcgen05-reg": 0, "tcgen05-cpasync": 1, "tcgen05-ws": 2, "tcgen05-tmem": 3}.get(request.param, -1))
     yield request.param
     if request.param != "mma":
         assert lib.d3f_gemm_tcgen05_failed() == 0, "a tcgen05 GEMM gave up waiting on its mbarrier"
     lib.d3f_set_gemm_impl(1)
-    lib.d3f_set_gemm_pipeline(-1)
 
 
 @pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False)])
@@ -146,41 +134,7 @@ def test_leaky_backward_colsum(cuda, M, N):
     assert float((db.double() - ref.double().sum(0)).abs().max()) < 2e-5 * max(1.0, float(ref.double().sum(0).abs().max()))
 
 
-@pytest.fixture
-def skinny(cuda):
-    from d3feat.pytorch_b200 import _lib
-    lib = _lib.load()
-    lib.d3f_set_gemm_skinny(2)      # every problem the kernel takes
-    yield lib
-    lib.d3f_set_gemm_skinny(-1)
-
-
-@pytest.mark.parametrize("M,N,K,tb", [(40000, 32, 480, False), (13312, 64, 960, False), (13312, 32, 480, False),
-                                      (2816, 64, 960, False), (4100, 20, 48, False), (2049, 64, 16, False),
-                                      (40000, 32, 384, True), (5000, 64, 256, True), (70000, 33, 496, False)])
-def test_skinny_gemm_matches_fp64(skinny, cuda, M, N, K, tb):
-    """B-resident mma.sync kernel (gemm_skinny.cu): fp32 accuracy, row scale + bias + LeakyReLU epilogue, bit-identical
-    rows whatever the row count (forward determinism), ragged M / N."""
-    from d3feat.pytorch_b200 import ops
-    rng = np.random.default_rng(M + 3 * N + K)
-    A = rng.standard_normal((M, K)).astype(np.float32)
-    B = (rng.standard_normal((N, K) if tb else (K, N)) / np.sqrt(K)).astype(np.float32)
-    rs = (rng.random(M) + 0.5).astype(np.float32)
-    b = rng.standard_normal(N).astype(np.float32)
-    opB = B.T.astype(np.float64) if tb else B.astype(np.float64)
-    z = rs[:, None] * (A.astype(np.float64) @ opB) + b
-    ref = np.where(z > 0, z, 0.1 * z)
-    Ag, Bg = torch.from_numpy(A).to(cuda), torch.from_numpy(B).to(cuda)
-    kw = dict(row_scale=torch.from_numpy(rs).to(cuda), bias=torch.from_numpy(b).to(cuda), slope=0.1, deterministic=True)
-    got = ops.gemm(Ag, Bg, False, tb, **kw)
-    assert rel_err(got.cpu(), ref) < 2e-6 * max(1.0, np.sqrt(K) / 8)
-    half = ops.gemm(Ag[: M // 2 + 3].contiguous(), Bg, False, tb, row_scale=kw["row_scale"][: M // 2 + 3].contiguous(),
-                    bias=kw["bias"], slope=0.1, deterministic=True)
-    if M // 2 + 3 >= 2048:      # still routed to the skinny kernel: same bits
-        assert torch.equal(got[: M // 2 + 3], half)
-
-
-def test_skinny_gemm_blocked_weight_transpose(skinny, cuda):
+def test_gemm_blocked_weight_transpose(cuda):
     """The KPConv data-gradient GEMM: dx = G [Ns, K*Cout] x W^T with W [K, Cin, Cout] addressed block-wise."""
     rng = np.random.default_rng(9)
     ns, Kp, cin, cout = 5000, 15, 32, 64

@@ -11,9 +11,10 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4  # BASELINE.json north_star: descriptors and loss within 1e-4 relative, fp32
 
 
-@pytest.fixture(params=[0, 1, 2], ids=["v1", "v2-ffma", "v2-mma"])
+@pytest.fixture(params=[1, 2, 3], ids=["ffma+gemm", "mma+gemm", "fused"])
 def kp_impl(request, built_lib):
-    """Every KPConv parity case runs on all three gather-kernel generations (d3f_set_kpconv_impl)."""
+    """Every KPConv parity case runs on every forward path (debug selector d3f_set_kpconv_impl): gather kernel with FFMA or
+    mma.sync correlation + contraction GEMM, and the fused kernel (falls back to mma+gemm where a layer is not eligible)."""
     built_lib.d3f_set_kpconv_impl(request.param)
     assert built_lib.d3f_get_kpconv_impl() == request.param
     yield request.param
