@@ -6,6 +6,7 @@
 #include "../../../include/d3feat_b200.h"
 
 void d3f_set_error(const char* fmt, ...);
+int* d3f_fail_flag_device();   // gemm_tcgen05.cu: device int raised when a tensor-core kernel gives up on an mbarrier
 
 #define D3F_CHECK_CUDA(expr)                                                                   \
     do {                                                                                       \

@@ -379,9 +379,16 @@ extern "C" int d3f_tc5_timing(unsigned long long* out32) {
 // Asynchronous, capturable form: out[0] = 1 if any tcgen05 GEMM of this process gave up waiting on an mbarrier (its
 // output tile was poisoned with NaN), copied device-to-device on `stream` so that a sync-free pipeline can fold it into
 // its status vector (engine.PairStep).
-extern "C" int d3f_gemm_status_snapshot(int32_t* out, d3f_stream stream) {
+// device address of the library-wide "a tensor-core kernel timed out on an mbarrier" flag (also raised by kpconv_fused.cu)
+int* d3f_fail_flag_device() {
     static int* addr = nullptr;
-    if (!addr) D3F_CHECK_CUDA(cudaGetSymbolAddress((void**)&addr, g_tc5_fail));
+    if (!addr && cudaGetSymbolAddress((void**)&addr, g_tc5_fail) != cudaSuccess) addr = nullptr;
+    return addr;
+}
+
+extern "C" int d3f_gemm_status_snapshot(int32_t* out, d3f_stream stream) {
+    int* addr = d3f_fail_flag_device();
+    D3F_REQUIRE(addr, D3F_ERR_CUDA, "cudaGetSymbolAddress failed");
     D3F_REQUIRE(out, D3F_ERR_INVALID, "null pointer");
     D3F_CHECK_CUDA(cudaMemcpyAsync(out, addr, sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return D3F_OK;

@@ -118,9 +118,13 @@ extern "C" int d3f_kpconv_forward_ex(const float* q_pts, const float* s_pts, con
     int rc = kp_check(nq, ns, H, K, cin, cout);
     if (rc) return rc;
     if (nq == 0) return D3F_OK;
-    D3F_REQUIRE(q_pts && s_pts && (inds || H == 0) && x && weights && kernel_points && out && wf && inv_n,
+    D3F_REQUIRE(q_pts && s_pts && (inds || H == 0) && x && weights && kernel_points && out && inv_n,
                 D3F_ERR_INVALID, "null pointer");
     D3F_REQUIRE(!modulations || wf_unmod, D3F_ERR_INVALID, "wf_unmod is required with modulations");
+    const bool fused = kp_impl() == 3 && !deformed && !modulations && influence == D3F_INFLUENCE_LINEAR &&
+                       aggregation == D3F_AGGREGATION_SUM && kpf_fused_eligible(H, K, cin, cout) && ns > 0 &&
+                       (((size_t)x | (size_t)out | (size_t)wf) & 15) == 0 && (long long)ns * cin < (1LL << 31);
+    D3F_REQUIRE(wf || fused, D3F_ERR_INVALID, "wf may only be NULL for layers d3f_kpconv_fused_eligible() accepts");
     D3F_REQUIRE(influence >= 0 && influence <= 2 && aggregation >= 0 && aggregation <= 1, D3F_ERR_INVALID, "bad mode");
     KpWs w;
     const size_t need = kp_layout(&w, workspace, workspace_bytes, nq, ns, K, cin, cout);
@@ -130,6 +134,15 @@ extern "C" int d3f_kpconv_forward_ex(const float* q_pts, const float* s_pts, con
         D3F_CHECK_LAUNCH();
     }
     if (g_kp_ev0) D3F_CHECK_CUDA(cudaEventRecord(g_kp_ev0, stream));
+    if (fused) {
+        // gather + correlation + contraction + 1/n + bias + LeakyReLU: one launch, wf only written on request
+        Kp2Args a2{q_pts, s_pts, inds, (long long)ld_inds, x, kernel_points, nullptr, w.rowpos,
+                   nq, ns, H, K, cin, kp_extent, influence, aggregation, idx_is_64 ? 1 : 0, 0};
+        rc = kpf_fused_launch(a2, weights, bias, leaky_relu, slope, out, inv_n, wf, stream);
+        if (rc) return rc;
+        if (g_kp_ev1) D3F_CHECK_CUDA(cudaEventRecord(g_kp_ev1, stream));
+        return D3F_OK;
+    }
     D3F_REQUIRE((long long)ns * cin < (1LL << 31), D3F_ERR_UNSUPPORTED, "Ns * Cin must stay below 2^31");
     {
         Kp2Args a2{q_pts, s_pts, inds, (long long)ld_inds, x, kernel_points, modulations, w.rowpos,
@@ -233,8 +246,8 @@ extern "C" int d3f_kpconv_backward_ex(const float* q_pts, const float* s_pts, co
                               deformed ? grad_modulations : nullptr, stream);
 }
 
-// 1 if d3f_kpconv_forward[_ex] runs this layer shape as ONE fused kernel (rigid, unmodulated layers only)
+// 1 if d3f_kpconv_forward[_ex] runs this layer shape as ONE fused kernel (rigid, unmodulated, linear influence, sum
+// aggregation; and the fused path is selected)
 extern "C" int d3f_kpconv_fused_eligible(int n_neighbors, int K, int c_in, int c_out) {
-    (void)n_neighbors; (void)K; (void)c_in; (void)c_out;
-    return 0;
+    return kp_impl() == 3 && kpf_fused_eligible(n_neighbors, K, c_in, c_out) ? 1 : 0;
 }

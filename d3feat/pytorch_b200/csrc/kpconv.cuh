@@ -25,3 +25,9 @@ struct Kp2tArgs {
 bool kp2t_supported(int nq, int cout);
 // G [ns, K, cout] = sum over listing queries of w * inv_n * grad_out rows
 int kp2t_correlate_launch(const Kp2tArgs& a, float* G, cudaStream_t stream);
+
+// fused forward (kpconv_fused.cu): gather + correlation + tcgen05 contraction + 1/n, bias, LeakyReLU in one kernel.
+// wf may be null (not written).  Needs 16-byte aligned x / out and Ns * Cin < 2^31.
+bool kpf_fused_eligible(int H, int K, int cin, int cout);
+int kpf_fused_launch(const Kp2Args& g, const float* weights, const float* bias, int act, float slope, float* out,
+                     float* inv_n, float* wf, cudaStream_t stream);

@@ -83,6 +83,26 @@ __global__ void nb_scatter_kernel(const float* __restrict__ s, int ns, const int
     sorted[dst] = make_float4(s[3 * i], s[3 * i + 1], s[3 * i + 2], __int_as_float(i));
 }
 
+// ascending bitonic sort of cand[0, m) by one warp (entries beyond m up to the next power of two are set to ~0)
+__device__ __forceinline__ void nb_warp_sort(unsigned long long* cand, int m, int lane) {
+    int n2 = 1;
+    while (n2 < m) n2 <<= 1;
+    for (int t = m + lane; t < n2; t += 32) cand[t] = ~0ULL;
+    __syncwarp();
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = lane; t < (n2 >> 1); t += 32) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const unsigned long long a = cand[i], c = cand[l];
+                const bool up = (i & k) == 0;
+                if ((a > c) == up) { cand[i] = c; cand[l] = a; }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 template <bool IDX64>
 __global__ void nb_query_kernel(const float* __restrict__ q, const int32_t* __restrict__ q_len, int nb, int nq,
                                 int ns, float inv_cs, float r2, const unsigned long long* __restrict__ keys,
@@ -96,7 +116,8 @@ __global__ void nb_query_kernel(const float* __restrict__ q, const int32_t* __re
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qi = blockIdx.x * (blockDim.x >> 5) + warp;
     unsigned long long* cand = cand_all + (size_t)warp * cap;
-    int count = 0;
+    int count = 0, nbuf = 0;      // in-range supports seen / candidates currently buffered
+    const bool can_compact = out != nullptr && max_cols + 32 <= cap;
     int st;
     const int b = qi < nq ? d3f_batch_of(qi, q_len, nb, &st) : -1;
     if (qi < nq && b < 0 && out != nullptr) {
@@ -139,34 +160,32 @@ __global__ void nb_query_kernel(const float* __restrict__ q, const int32_t* __re
                 ck = ((unsigned long long)__float_as_uint(d2) << 32) | (uint32_t)__float_as_int(p.w);
             }
             const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+            const int nh = __popc(bal);
+            // The buffer holds `cap` candidates.  Only the max_cols nearest are ever written, so when it would overflow
+            // it is compacted in place: sort, keep the max_cols smallest keys seen so far, go on.  A row with ANY number
+            // of in-range supports (deformable radii: hundreds) therefore still yields its exact nearest max_cols; the
+            // overflow flag is left for the case that cannot be compacted (max_cols + 32 > cap: count-only / untruncated
+            // calls, which the drop-in wrapper retries with a larger buffer).
+            if (nbuf + nh > cap && can_compact) {          // warp-uniform
+                __syncwarp();
+                nb_warp_sort(cand, nbuf, lane);
+                nbuf = min(nbuf, max_cols);
+            }
             if (hit) {
-                int pos = count + __popc(bal & ((1u << lane) - 1u));
+                int pos = nbuf + __popc(bal & ((1u << lane) - 1u));
                 if (pos < cap) cand[pos] = ck;
             }
-            count += __popc(bal);
+            nbuf += nh;
+            count += nh;
         }
         if (lane == 0) {
             atomicMax(&s_max, count);
-            if (count > cap) s_ovf = 1;
+            if (nbuf > cap) s_ovf = 1;
         }
         if (out != nullptr) {
-            const int m = min(count, cap);
-            int n2 = 1;
-            while (n2 < m) n2 <<= 1;
-            for (int t = m + lane; t < n2; t += 32) cand[t] = ~0ULL;
+            const int m = min(nbuf, cap);
             __syncwarp();
-            for (int k = 2; k <= n2; k <<= 1) {
-                for (int j = k >> 1; j > 0; j >>= 1) {
-                    for (int t = lane; t < (n2 >> 1); t += 32) {
-                        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                        const int l = i | j;
-                        const unsigned long long a = cand[i], c = cand[l];
-                        const bool up = (i & k) == 0;
-                        if ((a > c) == up) { cand[i] = c; cand[l] = a; }
-                    }
-                    __syncwarp();
-                }
-            }
+            nb_warp_sort(cand, m, lane);
             for (int col = lane; col < max_cols; col += 32) {
                 const int v = col < m ? (int)(uint32_t)(cand[col] & 0xffffffffULL) : pad_index;
                 if (IDX64) ((long long*)out)[(size_t)qi * max_cols + col] = v;

@@ -152,9 +152,18 @@ def grid_subsample_raw(points, lengths, sample_dl, out_capacity):
 
 
 # --------------------------------------------------------------------------- KPConv
+def kpconv_fused_eligible(H, K, cin, cout, deformed=False, modulations=None, influence="linear", aggregation="sum"):
+    """True if d3f_kpconv_forward_ex runs this layer as ONE fused kernel (then `wf` is optional)."""
+    return (not deformed and modulations is None and influence == "linear" and aggregation == "sum"
+            and bool(_lib.load().d3f_kpconv_fused_eligible(int(H), int(K), int(cin), int(cout))))
+
+
 def kpconv_forward(q_pts, s_pts, inds, x, weights, kernel_points, extent, influence, aggregation,
-                   deformed=False, modulations=None, want_min_d2=False, bias=None, slope=None):
-    """d3f_kpconv_forward_ex: out = act(KPConv(...) + bias) with act = LeakyReLU(slope) when slope is given."""
+                   deformed=False, modulations=None, want_min_d2=False, bias=None, slope=None, need_wf=True):
+    """d3f_kpconv_forward_ex: out = act(KPConv(...) + bias) with act = LeakyReLU(slope) when slope is given.
+    need_wf=False: the caller does not need the kernel-point-weighted features [Nq, K, Cin] (inference, or a backward
+    that works from the transposed neighbour lists); on the fused path they are then never written (returned as None),
+    on the two-kernel path they remain the contraction's input."""
     lib = _lib.load()
     q_pts, s_pts, x = _cuda_f32(q_pts, "q_pts"), _cuda_f32(s_pts, "s_pts"), _cuda_f32(x, "x")
     weights, kernel_points = _cuda_f32(weights, "weights"), _cuda_f32(kernel_points, "kernel_points")
@@ -170,7 +179,9 @@ def kpconv_forward(q_pts, s_pts, inds, x, weights, kernel_points, extent, influe
     if x.shape[0] != ns or x.shape[1] != cin:
         raise RuntimeError("KPConv: x must be [n_supports, in_channels] = [%d, %d], got %s" % (ns, cin, tuple(x.shape)))
     out = torch.empty((nq, cout), dtype=torch.float32, device=dev)
-    wf = torch.empty((nq, K, cin), dtype=torch.float32, device=dev)
+    skip_wf = (not need_wf) and ns > 0 and nq > 0 and kpconv_fused_eligible(H, K, cin, cout, deformed, modulations, influence,
+                                                                            aggregation)
+    wf = None if skip_wf else torch.empty((nq, K, cin), dtype=torch.float32, device=dev)
     wf_un = torch.empty_like(wf) if modulations is not None else None
     inv_n = torch.empty(nq, dtype=torch.float32, device=dev)
     min_d2 = torch.empty((nq, K), dtype=torch.float32, device=dev) if (deformed and want_min_d2) else None

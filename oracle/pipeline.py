@@ -9,8 +9,25 @@ import torch
 from . import cpu, model_ref
 
 
-def cpu_collate(data, config, limits, impl="port"):
-    """collate_fn_descriptor (dataloader.py:69-189) on the CPU oracle (`impl`: 'ref' = reference C++)."""
+def canonical_tie_order(q, s, idx):
+    """Order every neighbour row by (d2, index).  The reference sorts a row by d2 with std::sort (nanoflann.hpp:1287),
+    which is not stable: rows holding EXACTLY equal fp32 d2 values (3 rows of 40 000 on a 20k+20k pair) come out in an
+    arbitrary order inside each equal-d2 run.  The documented tie contract of the device path (and of the plain-C port)
+    is ascending index inside a run; this reorders ONLY inside runs of equal d2 (reference arithmetic, no FMA)."""
+    ns = s.shape[0]
+    sp = np.concatenate([s, np.full((1, 3), np.inf, np.float32)], 0)
+    d = (q[:, None, :] - sp[np.minimum(idx, ns)]).astype(np.float32)
+    with np.errstate(invalid="ignore", over="ignore"):
+        d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+    d2 = np.where(idx >= ns, np.inf, d2).astype(np.float32)
+    order = np.lexsort((idx, d2))
+    return np.take_along_axis(idx, order, axis=1)
+
+
+def cpu_collate(data, config, limits, impl="port", canonical_ties=True):
+    """collate_fn_descriptor (dataloader.py:69-189) on the CPU oracle (`impl`: 'ref' = reference C++).
+    canonical_ties: apply `canonical_tie_order` to the reference's rows BEFORE the truncation to `limits` columns
+    (the port already orders ties by index)."""
     pts0, pts1, feat0, feat1, sel_corr, dist_keypts = data
     pts = np.concatenate([pts0, pts1]).astype(np.float32)
     lens = np.array([len(pts0), len(pts1)], np.int32)
@@ -20,7 +37,11 @@ def cpu_collate(data, config, limits, impl="port"):
 
     def nb(q, s, ql, sl, r, lim):
         m = cpu.batch_query(q, s, ql, sl, r, impl=impl)
-        return torch.from_numpy(m[:, :lim] if lim > 0 else m).long()
+        if canonical_ties and impl == "ref" and m.shape[1] > 1:
+            # chunked: the [rows, cols, 3] difference tensor of a wide (deformable-radius) matrix is large
+            m = np.concatenate([canonical_tie_order(q[i:i + 8192], s, m[i:i + 8192]) for i in range(0, m.shape[0], 8192)]) \
+                if m.shape[0] else m
+        return torch.from_numpy(np.ascontiguousarray(m[:, :lim] if lim > 0 else m)).long()
 
     for bi, block in enumerate(arch):
         if "global" in block or "upsample" in block:
@@ -65,7 +86,7 @@ def cpu_pair_step(data, sd, config, limits, impl="ref", backward=True, sgd=None)
     updated in place together with `sd`).  Returns (seconds per stage dict, loss value)."""
     t = {}
     t0 = time.perf_counter()
-    batch = cpu_collate(data, config, limits, impl=impl)
+    batch = cpu_collate(data, config, limits, impl=impl, canonical_ties=False)   # timed: the reference's own row order
     t["collate"] = time.perf_counter() - t0
     params = {k: (v.detach().clone().requires_grad_(backward and "kernel_points" not in k)) for k, v in sd.items()}
     t0 = time.perf_counter()

@@ -162,3 +162,46 @@ def test_kpconv_backward_over_transposed_lists(cuda, nq, ns, H, cin, cout, idx_d
         grads.append((xg.grad.cpu(), Wg.grad.cpu()))
     assert rel_err(grads[1][0], x.grad) < TOL and rel_err(grads[1][1], W.grad) < TOL
     assert rel_err(grads[1][0], grads[0][0]) < 2e-5
+
+
+@pytest.mark.parametrize("nq,ns,H,idx_dtype,strided", [(6000, 5000, 35, torch.int32, False), (2370, 9000, 35, torch.int64, True),
+                                                       (16, 40, 48, torch.int32, False), (4737, 300, 8, torch.int64, False),
+                                                       (1, 1, 1, torch.int32, False), (333, 500, 41, torch.int32, True)])
+def test_fused_kernel_many_batches_vs_oracle(cuda, built_lib, nq, ns, H, idx_dtype, strided):
+    """The fused kernel (gather + correlation + tcgen05 contraction, W^T in tensor memory) over several batches per CTA,
+    partial last batches, shadow-only rows, int32/int64 and strided index rows: output with bias + LeakyReLU, 1/n and the
+    optional wf against the CPU oracle; bit-identical run to run; wf == the two-kernel path's wf."""
+    from oracle import model_ref
+    from d3feat.pytorch_b200 import ops
+    built_lib.d3f_set_kpconv_impl(3)
+    try:
+        assert built_lib.d3f_kpconv_fused_eligible(H, 15, 32, 32) == 1
+        rng = np.random.default_rng(nq + H)
+        q = torch.from_numpy((rng.random((nq, 3)) * 0.2).astype(np.float32))
+        s = torch.from_numpy((rng.random((ns, 3)) * 0.2).astype(np.float32))
+        wide = rng.integers(0, ns + 1, size=(nq, H + 5)).astype(np.int64)          # ns = shadow
+        wide[rng.random(nq) < 0.05] = ns                                         # all-shadow rows
+        wide = np.sort(wide, axis=1) if nq % 2 else wide                         # padding at the end (typical) or scattered
+        inds = torch.from_numpy(wide)[:, :H] if strided else torch.from_numpy(np.ascontiguousarray(wide[:, :H]))
+        x = torch.from_numpy(rng.standard_normal((ns, 32)).astype(np.float32))
+        x[rng.choice(ns, max(ns // 10, 1), replace=False)] *= -1.0                 # rows with a non-positive channel sum
+        W = torch.from_numpy((rng.standard_normal((15, 32, 32)) / np.sqrt(480)).astype(np.float32))
+        kp = torch.from_numpy((_inputs.unit_kernel_points() * 0.075).astype(np.float32))
+        b = torch.from_numpy(rng.standard_normal(32).astype(np.float32) * 0.1)
+        ref = torch.nn.functional.leaky_relu(model_ref.kpconv_rigid(q, s, inds, x, W, kp, 0.06) + b, 0.1)
+        g = lambda t: t.to(cuda)
+        ig = g(torch.from_numpy(wide)).to(idx_dtype)
+        ig = ig[:, :H] if strided else ig[:, :H].contiguous()
+        args = (g(q), g(s), ig, g(x), g(W), g(kp), 0.06, "linear", "sum")
+        out, wf, _, inv_n, _ = ops.kpconv_forward(*args, bias=g(b), slope=0.1, need_wf=True)
+        out2, wf2, _, _, _ = ops.kpconv_forward(*args, bias=g(b), slope=0.1, need_wf=False)
+        assert wf2 is None and torch.equal(out, out2)
+        scale = max(float(ref.abs().max()), 1e-6)
+        assert float((out.cpu() - ref).abs().max()) / scale < TOL
+        built_lib.d3f_set_kpconv_impl(2)
+        out3, wf3, _, inv3, _ = ops.kpconv_forward(*args, bias=g(b), slope=0.1)
+        assert torch.equal(inv_n, inv3)
+        assert float((wf - wf3).abs().max()) <= 1e-5 * max(float(wf3.abs().max()), 1e-6)
+        assert built_lib.d3f_gemm_tcgen05_failed() == 0
+    finally:
+        built_lib.d3f_set_kpconv_impl(-1)

@@ -55,6 +55,26 @@ def test_capacity_overflow_is_retried(cuda, oracle_cpu):
     assert np.array_equal(got, ref[:, :5])
 
 
+def test_static_call_compacts_rows_far_above_the_candidate_buffer(cuda, oracle_cpu):
+    """One d3f_radius_neighbors call (no retry, as inside the CUDA graph) with rows holding 300-700 in-range supports,
+    a 64-entry candidate buffer and 20 columns: exact nearest 20, overflow flag clear, max count still reported."""
+    import torch
+    from d3feat.pytorch_b200 import ops
+    rng = np.random.default_rng(11)
+    p = (rng.random((6000, 3)) * 0.5).astype(np.float32)
+    lens = np.array([3500, 2500], np.int32)
+    ref = oracle_cpu.batch_query(p, p, lens, lens, 0.16)
+    assert ref.shape[1] > 300
+    t = torch.from_numpy(p).to(cuda)
+    tl = torch.from_numpy(lens).to(cuda)
+    idx, info = ops.radius_neighbors_raw(t, t, tl, tl, 0.16, 20, torch.int32, 64, False)
+    assert np.array_equal(idx.cpu().numpy(), ref[:, :20])
+    assert info[:2].tolist() == [ref.shape[1], 0]
+    # a buffer that cannot be compacted (max_cols + 32 > capacity) still raises the flag
+    _, info = ops.radius_neighbors_raw(t, t, tl, tl, 0.16, 40, torch.int32, 64, False)
+    assert int(info[1]) == 1
+
+
 def test_exact_ties_are_index_ordered(cuda, oracle_cpu):
     # integer lattice: masses of exactly equal distances
     g = np.stack(np.meshgrid(*[np.arange(9)] * 3, indexing="ij"), -1).reshape(-1, 3).astype(np.float32) * 0.05

@@ -1,5 +1,6 @@
-"""A/B micro-benchmark of the KPConv gather / scatter kernels and the contraction GEMM on the real pyramid of one
-synthetic 20k+20k pair: python tools/kpconv_micro.py   (CUDA events around `reps` back-to-back calls, L2-warm)."""
+"""A/B micro-benchmark of the KPConv forward paths on the real pyramid of one synthetic 20k+20k pair:
+python tools/kpconv_micro.py   -> per layer: gather/fused kernel alone (events inside the C call) and the whole op,
+L2-warm (back to back) and L2-cold (256 MiB flush write before every call)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -14,21 +15,41 @@ cfg = default_config()
 limits = [35, 42, 42, 45, 47]
 batch = collate_fn_descriptor([synthetic.fragment_pair(20000, seed=0)], cfg, limits)
 kp = torch.from_numpy(np.random.default_rng(0).standard_normal((15, 3)).astype(np.float32) * 0.03).to(dev)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
-def timed(fn, reps=20):
+def timed(fn, reps=20, cold=False):
     fn(); torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    tot = 0.0
+    evs = []
     for _ in range(reps):
+        if cold:
+            flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in evs) / reps * 1e3   # us
+
+
+def kernel_alone(fn, reps=10, cold=False):
+    ts = []
+    for _ in range(reps):
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record(); ev[1].record()
+        if cold:
+            flush.fill_(1)
+        lib.d3f_kpconv_set_gather_events(ev[0].cuda_event, ev[1].cuda_event)
         fn()
-    e1.record(); torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps * 1e3   # us
+        lib.d3f_kpconv_set_gather_events(None, None)
+        torch.cuda.synchronize()
+        ts.append(ev[0].elapsed_time(ev[1]) * 1e3)
+    return float(np.median(ts))
 
 
 cases = [("L0 32->32", 0, "neighbors", 32, 32), ("L0->1 strided 32->32", 0, "pools", 32, 32), ("L1 64->64", 1, "neighbors", 64, 64),
          ("L2 128->128", 2, "neighbors", 128, 128), ("L0 1->64", 0, "neighbors", 1, 64)]
-print("%-22s %-10s %10s %10s %10s" % ("layer", "impl", "gather us", "fwd op us", "bwd op us"))
+print("%-22s %-12s %12s %12s %12s %12s  %s" % ("layer", "impl", "kern warm", "kern cold", "op warm", "op cold", "logical GB/s (kernel, cold)"))
 for name, lvl, kind, cin, cout in cases:
     inds = batch[kind][lvl].to(torch.int32)
     s = batch["points"][lvl]
@@ -36,63 +57,25 @@ for name, lvl, kind, cin, cout in cases:
     r = cfg.first_subsampling_dl * cfg.conv_radius * (2 ** lvl)
     x = torch.randn(s.shape[0], cin, device=dev)
     W = torch.randn(15, cin, cout, device=dev) / (15 * cin) ** 0.5
+    b = torch.randn(cout, device=dev)
     kpl = kp * (2 ** lvl)
-    g = torch.randn(q.shape[0], cout, device=dev)
-    tr = ops.neighbors_transpose(inds, s.shape[0])
-    t_tr = timed(lambda: ops.neighbors_transpose(inds, s.shape[0]))
-    print("%-22s neighbors_transpose: %.1f us" % (name, t_tr))
-    for impl, label, env in ((0, "v1", None), (1, "v2-ffma", None), (2, "v2-mma", None), (2, "v2-mma/scalar-red", "scalar"),
-                             (2, "v2-mma/transposed", "t"), (2, "v2-mma/transp+skinny", "sk")):
-        lib.d3f_set_gemm_skinny(2 if env == "sk" else 0)
+    ext = 0.8 * r
+    nq, H = q.shape[0], inds.shape[1]
+    logical = nq * H * (4 * cin + 16) + nq * (12 + 4 * cout) + 4 * 15 * cin * cout
+    outs = {}
+    for impl, label in ((1, "ffma+gemm"), (2, "mma+gemm"), (3, "fused")):
         lib.d3f_set_kpconv_impl(impl)
-        if hasattr(lib, "d3f_set_scatter_vec"):
-            lib.d3f_set_scatter_vec(0 if env == "scalar" else 2)
-        elif env == "scalar":
+        fused = impl == 3 and lib.d3f_kpconv_fused_eligible(H, 15, cin, cout)
+        if impl == 3 and not fused:
             continue
-        ext = 0.8 * r
-        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        ev[0].record(); ev[1].record()
-        out = ops.kpconv_forward(q, s, inds, x, W, kpl, ext, "linear", "sum")
-        t_f = timed(lambda: ops.kpconv_forward(q, s, inds, x, W, kpl, ext, "linear", "sum"))
-        # gather kernel alone: events recorded inside the C call (last call of a short loop)
-        lib.d3f_kpconv_set_gather_events(ev[0].cuda_event, ev[1].cuda_event)
-        for _ in range(3):
-            ops.kpconv_forward(q, s, inds, x, W, kpl, ext, "linear", "sum")
-        torch.cuda.synchronize()
-        lib.d3f_kpconv_set_gather_events(None, None)
-        t_g = ev[0].elapsed_time(ev[1]) * 1e3
-        _, wf, wf_un, inv_n, _ = out
-        t_b = timed(lambda: ops.kpconv_backward(q, s, inds, x, W, kpl, ext, "linear", "sum", False, None, wf, wf_un, inv_n, g,
-                                                cin > 1, True, False, False, transpose=tr if env in ("t", "sk") else None))
-        print("%-22s %-18s %10.1f %10.1f %10.1f" % (name, label, t_g, t_f, t_b))
+        fn = lambda: ops.kpconv_forward(q, s, inds, x, W, kpl, ext, "linear", "sum", bias=b, slope=0.1, need_wf=not fused)
+        outs[impl] = fn()[0]
+        kw, kc = kernel_alone(fn), kernel_alone(fn, cold=True)
+        ow, oc = timed(fn), timed(fn, cold=True)
+        print("%-22s %-12s %12.1f %12.1f %12.1f %12.1f  %8.0f" % (name, label, kw, kc, ow, oc, logical / kc / 1e3))
+    if 3 in outs:
+        d = (outs[3] - outs[2]).abs().max() / outs[2].abs().max()
+        print("%-22s fused vs mma+gemm max rel diff %.2e" % (name, float(d)))
 lib.d3f_set_kpconv_impl(-1)
-lib.d3f_set_gemm_skinny(-1)
-
-print("\nGEMM pipelines (us per call, back to back):")
-shapes = [(40000, 32, 480, False, False), (13312, 32, 480, False, False), (13312, 64, 960, False, False), (40000, 480, 32, False, True),
-          (480, 32, 40000, True, False), (40000, 128, 32, False, True), (40000, 32, 128, False, True), (40000, 32, 384, False, True),
-          (2816, 128, 1920, False, False), (768, 1024, 3072, False, True), (256, 512, 7680, False, False), (7680, 512, 256, True, False)]
-for (M, N, K, ta, tb) in shapes:
-    a = torch.randn((K, M) if ta else (M, K), device=dev)
-    b = torch.randn((N, K) if tb else (K, N), device=dev)
-    row = []
-    pipes = (0, 1, 2, 3) if os.environ.get("D3F_MICRO_TMEM", "1") == "1" else (0, 1, 2)   # 3 = experimental A-in-TMEM kernel (tc8)
-    for pipe in (0, 1, 2):
-        lib.d3f_set_gemm_pipeline(pipe)
-        for det in (False, True):
-            row.append(timed(lambda: ops.gemm(a, b, ta, tb, deterministic=det)))
-    lib.d3f_set_gemm_pipeline(-1)
-    lib.d3f_set_gemm_skinny(2)
-    row.append(timed(lambda: ops.gemm(a, b, ta, tb, deterministic=True)))
-    lib.d3f_set_gemm_skinny(-1)
-    t8 = None
-    if 3 in pipes:
-        lib.d3f_set_gemm_pipeline(3)
-        t8 = (timed(lambda: ops.gemm(a, b, ta, tb, deterministic=False)), timed(lambda: ops.gemm(a, b, ta, tb, deterministic=True)))
-        lib.d3f_set_gemm_pipeline(-1)
-    fl = 2.0 * M * N * K
-    print("M=%6d N=%5d K=%6d ta=%d tb=%d | reg: %6.1f (det %6.1f) | cp.async: %6.1f (det %6.1f) | warp-spec: %6.1f (det %6.1f) | skinny(if eligible): %6.1f | %.1f TFLOP/s best"
-          % (M, N, K, ta, tb, row[0], row[1], row[2], row[3], row[4], row[5], row[6], fl / min(row) / 1e6)
-          + ("" if t8 is None else " | tmem-A (tc8): %6.1f (det %6.1f)" % t8))
 if lib.d3f_gemm_tcgen05_failed() != 0:
-    print("WARNING: a tcgen05 GEMM gave up waiting on an mbarrier")
+    print("WARNING: a tensor-core kernel gave up waiting on an mbarrier")
