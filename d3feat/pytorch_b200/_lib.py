@@ -39,6 +39,8 @@ SIGNATURES = {
     "d3f_kpconv_backward_ex": (c_i, [c_p, c_p, c_p, c_i, c_i64, c_p, c_p, c_p, c_i, c_p,
                                      c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_i,
                                      c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "d3f_kpconv_gather_transposed": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_i, c_p, c_p]),
+    "d3f_kpconv_grads_from_gathered": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
     "d3f_neighbors_transpose_workspace_bytes": (c_sz, [c_i]),
     "d3f_neighbors_transpose": (c_i, [c_p, c_i, c_i64, c_i, c_i, c_i, c_p, c_p, c_p, c_sz, c_p]),
     "d3f_set_kpconv_impl": (None, [c_i]),

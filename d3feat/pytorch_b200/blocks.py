@@ -50,13 +50,21 @@ class _KPConvFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q_pts, s_pts, inds, x, weights, kpoints, modulations, extent, influence, aggregation,
                 deformed, want_min_d2, bias=None, slope=None, t_off=None, t_src=None, dsts=(None, None)):
+        # with transposed neighbour lists a rigid layer's backward works from the gather over those lists alone (grad_x AND
+        # grad_W): the kernel-point-weighted features wf are then not needed, and the fused kernel never writes them
+        lists = (t_off is not None and t_src is not None and inds.shape[1] > 0 and q_pts.shape[0] > 0 and s_pts.shape[0] > 0
+                 and ops.kpconv_fused_eligible(inds.shape[1], weights.shape[0], weights.shape[1], weights.shape[2],
+                                               deformed, modulations, influence, aggregation))
         out, wf, wf_un, inv_n, min_d2 = ops.kpconv_forward(q_pts, s_pts, inds, x, weights, kpoints, extent,
                                                            influence, aggregation, deformed, modulations,
-                                                           want_min_d2, bias, slope)
+                                                           want_min_d2, bias, slope, need_wf=not lists)
+        if lists:
+            wf = None
         ctx.save_for_backward(q_pts, s_pts, inds, x, weights, kpoints, modulations, wf, wf_un, inv_n,
                               out if slope is not None else None)
         ctx.cfg = (extent, influence, aggregation, deformed, slope)
         ctx.transpose = (t_off, t_src) if (t_off is not None and t_src is not None) else None
+        ctx.lists = lists
         ctx.dsts = dsts     # (grad_weights, grad_bias) destinations inside a flat gradient buffer, or Nones
         if min_d2 is None:
             min_d2 = out.new_empty(0)
@@ -81,7 +89,19 @@ class _KPConvFunction(torch.autograd.Function):
                 x.float().contiguous(), weights.contiguous(), kpoints.float().contiguous(), extent, influence,
                 aggregation, deformed, modulations, wf, wf_un, inv_n, grad_out.contiguous())
         need_data = need[3] or (need[5] and deformed) or need[6]
-        if need[4] and need_data:
+        if ctx.lists:
+            # fused-forward layers kept no wf: G (the gather over the transposed lists) feeds both gradients, and the two
+            # GEMMs that consume it run as concurrent branches
+            G = ops.kpconv_gather_transposed(args[0], args[1], ctx.transpose, args[14], inv_n, args[5], weights.shape[2],
+                                             extent, influence, aggregation)
+            gkp = gmod = None
+            if need[3] and need[4]:
+                (_, gw), (gx, _) = ops.run_branches(
+                    lambda: ops.kpconv_grads_from_gathered(G, args[3], args[4], False, True, dst_w),
+                    lambda: ops.kpconv_grads_from_gathered(G, args[3], args[4], True, False), grad_out.device)
+            else:
+                gx, gw = ops.kpconv_grads_from_gathered(G, args[3], args[4], need[3], need[4], dst_w)
+        elif need[4] and need_data:
             # the weight gradient (one GEMM over wf) and the data-gradient chain are independent: two branches
             (_, gw, _, _), (gx, _, gkp, gmod) = ops.run_branches(
                 lambda: ops.kpconv_backward(*args, need_x=False, need_w=True, need_kp=False, need_mod=False, gw_out=dst_w),

@@ -208,7 +208,8 @@ tc_gemm_kernel(D3fGemm g) {
                     const int n = n0 + wn + ni * 8 + 2 * tq + e;
                     if (n >= g.N) continue;
                     float v = acc[mi][ni][half * 2 + e] * sc;
-                    float* dst = g.C + (size_t)m * g.ldc + n;
+                    float* dst = g.cblk ? g.C + (size_t)(n / g.cblk) * g.cblk_stride + (size_t)m * g.ldc + (n % g.cblk)
+                                        : g.C + (size_t)m * g.ldc + n;
                     if (atomic) { atomicAdd(dst, v); continue; }
                     if (g.bias) v += g.bias[n];
                     if (g.bias2) v += g.bias2[n];
@@ -269,6 +270,8 @@ int d3f_gemm_launch(const D3fGemm& in, bool ta, bool tb, cudaStream_t stream, fl
     const int tiles = d3f_ceil_div(g.M, BM) * d3f_ceil_div(g.N, BN);
     int splits = 1, kps;
     const bool plain = !g.bias && !g.act && !g.bias2 && !g.res;   // atomically combined partials cannot take an epilogue
+    D3F_REQUIRE(!g.cblk || (!det_ws && (g.cblk & 3) == 0 && g.N % g.cblk == 0 && g.K > 0), D3F_ERR_UNSUPPORTED,
+                "blocked C needs the plain (non-deterministic) path, cblk % 4 == 0 and N % cblk == 0");
     if (det_ws) {
         splits = det_splits(g.M, g.K);
         kps = splits > 1 ? DET_KPS : d3f_ceil_div(g.K > 0 ? g.K : 1, BK) * BK;
@@ -284,7 +287,8 @@ int d3f_gemm_launch(const D3fGemm& in, bool ta, bool tb, cudaStream_t stream, fl
         }
         kps = d3f_ceil_div(d3f_ceil_div(g.K > 0 ? g.K : 1, splits), BK) * BK;
         splits = d3f_ceil_div(g.K > 0 ? g.K : 1, kps);
-        if (splits > 1) D3F_CHECK_CUDA(cudaMemsetAsync(g.C, 0, sizeof(float) * (size_t)g.M * g.ldc, stream));
+        const size_t c_floats = g.cblk ? (size_t)(g.N / g.cblk) * g.cblk_stride : (size_t)g.M * g.ldc;
+        if (splits > 1) D3F_CHECK_CUDA(cudaMemsetAsync(g.C, 0, sizeof(float) * c_floats, stream));
     }
     g.k_per_split = kps;
     if (g.K == 0) {

@@ -21,6 +21,10 @@ struct D3fGemm {
     // (bblk = 0: plain).  KPConv backward reads W [K_pts, Cin, Cout] as B^T[c][k * Cout + o] this way without a
     // transposed copy of the weights; bblk must be a multiple of 32.
     int bblk; long long bblk_stride;
+    // C written in column blocks: element (m, n) lives at C[(n / cblk) * cblk_stride + m * ldc + n % cblk] (cblk = 0: plain;
+    // cblk a multiple of 4).  KPConv's weight gradient from the transposed gather, dW[k][c][o] = sum_j x[j][c] G[j][k*Cout+o],
+    // lands in the [K_pts, Cin, Cout] layout of the weights this way (cblk = Cout, cblk_stride = Cin*Cout, ldc = Cout).
+    int cblk; long long cblk_stride;
 };
 
 // C[M,N] = act(rs[m] * sum_k opA(m,k) * ks[k] * opB(k,n) + bias[n] + bias2[n] + res[m,n]);  ta: A stored [K,M];  tb: B stored [N,K]

@@ -295,7 +295,8 @@ tc5_gemm_kernel(D3fGemm g) {
                 continue;
             }
             const float sc = g.rs ? g.rs[row] : 1.0f;
-            float* dst = g.C + (size_t)row * g.ldc + n;
+            float* dst = g.cblk ? g.C + (size_t)(n / g.cblk) * g.cblk_stride + (size_t)row * g.ldc + (n % g.cblk)
+                                : g.C + (size_t)row * g.ldc + n;
             if (atomic) {
                 for (int e = 0; e < 4; ++e) if (n + e < g.N) atomicAdd(dst + e, xs[e] * sc);
                 continue;

@@ -196,7 +196,8 @@ extern "C" int d3f_kpconv_backward_ex(const float* q_pts, const float* s_pts, co
     int rc = kp_check(nq, ns, H, K, cin, cout);
     if (rc) return rc;
     D3F_REQUIRE(influence >= 0 && influence <= 2 && aggregation >= 0 && aggregation <= 1, D3F_ERR_INVALID, "bad mode");
-    const bool transposed = grad_x && t_offsets && t_src && !deformed && !modulations && kp2t_supported(nq, cout) && ns > 0 && nq > 0;
+    const bool transposed = (grad_x || grad_weights) && t_offsets && t_src && !deformed && !modulations &&
+                            kp2t_supported(nq, cout) && ns > 0 && nq > 0 && (cout & 3) == 0;
     // the scatter accumulates into grad_x with reductions; the transposed path's GEMM overwrites it
     if (grad_x && ns > 0 && !transposed)
         D3F_CHECK_CUDA(cudaMemsetAsync(grad_x, 0, sizeof(float) * (size_t)ns * cin, stream));
@@ -204,31 +205,46 @@ extern "C" int d3f_kpconv_backward_ex(const float* q_pts, const float* s_pts, co
         if (grad_weights) D3F_CHECK_CUDA(cudaMemsetAsync(grad_weights, 0, sizeof(float) * (size_t)K * cin * cout, stream));
         return D3F_OK;
     }
-    D3F_REQUIRE(q_pts && s_pts && (inds || H == 0) && x && weights && kernel_points && wf && inv_n && grad_out,
+    D3F_REQUIRE(q_pts && s_pts && (inds || H == 0) && x && weights && kernel_points && inv_n && grad_out,
                 D3F_ERR_INVALID, "null pointer");
     KpWs w;
     const size_t need = kp_layout(&w, workspace, workspace_bytes, nq, ns, K, cin, cout);
     D3F_REQUIRE(workspace && need <= workspace_bytes, D3F_ERR_WORKSPACE, "workspace too small");
     const int KC = K * cin;
+    const bool need_scatter = grad_x || (deformed && (grad_kernel_points || grad_modulations));
+    if (transposed) {
+        // atomic-free, and wf-free: G[j,k,o] = sum over the queries i that list support j of w * (1/n_i) * g[i,o]
+        // (forward-style gather over the transposed lists), then
+        //   grad_x[j,c]   = sum_{k,o} G[j,k,o] W[k,c,o]          (one GEMM, W addressed block-wise)
+        //   grad_W[k,c,o] = sum_j x[j,c] G[j,k,o]               (one GEMM, C written in the [K,Cin,Cout] layout)
+        // -- the weight gradient no longer needs the kernel-point-weighted features wf [Nq,K,Cin] of the forward pass,
+        // so the forward (fused kernel) never writes them.
+        float* G = w.dwf;
+        Kp2tArgs ta{q_pts, s_pts, t_offsets, t_src, grad_out, inv_n, kernel_points, nq, ns, K, cout, kp_extent, influence,
+                    aggregation};
+        rc = kp2t_correlate_launch(ta, G, stream);
+        if (rc) return rc;
+        if (grad_weights) {
+            D3fGemm g{cin, K * cout, ns, x, cin, G, K * cout, grad_weights, cout, nullptr, nullptr, nullptr, 0, 0.f, 0, nullptr,
+                      nullptr, nullptr, 0, 0, 0, cout, (long long)cin * cout};
+            rc = d3f_gemm_launch(g, true, false, stream);
+            if (rc) return rc;
+        }
+        if (grad_x) {
+            D3fGemm g{ns, cin, K * cout, G, K * cout, weights, cout, grad_x, cin, nullptr, nullptr, nullptr, 0, 0.f, 0, nullptr,
+                      nullptr, nullptr, 0, cout, (long long)cin * cout};
+            return d3f_gemm_launch(g, false, true, stream);
+        }
+        return D3F_OK;
+    }
+    D3F_REQUIRE(wf, D3F_ERR_INVALID, "wf is required without transposed neighbour lists");
     // dW[kc, o] = sum_i wf[i, kc] * inv_n[i] * g[i, o]
     if (grad_weights) {
         D3fGemm g{KC, cout, nq, wf, KC, grad_out, cout, grad_weights, cout, nullptr, inv_n, nullptr, 0, 0.f, 0, nullptr};
         rc = d3f_gemm_launch(g, true, false, stream);
         if (rc) return rc;
     }
-    const bool need_scatter = grad_x || (deformed && (grad_kernel_points || grad_modulations));
     if (!need_scatter) return D3F_OK;
-    if (transposed) {
-        // atomic-free: G[j,k,o] over the transposed lists, then grad_x[j,c] = sum_{k,o} G[j,k,o] W[k,c,o]
-        float* G = w.dwf;
-        Kp2tArgs ta{q_pts, s_pts, t_offsets, t_src, grad_out, inv_n, kernel_points, nq, ns, K, cout, kp_extent, influence,
-                    aggregation};
-        rc = kp2t_correlate_launch(ta, G, stream);
-        if (rc) return rc;
-        D3fGemm g{ns, cin, K * cout, G, K * cout, weights, cout, grad_x, cin, nullptr, nullptr, nullptr, 0, 0.f, 0, nullptr,
-                  nullptr, nullptr, 0, cout, (long long)cin * cout};
-        return d3f_gemm_launch(g, false, true, stream);
-    }
     // dwf[i, kc] = inv_n[i] * sum_o g[i, o] * W[kc, o]
     {
         D3fGemm g{nq, KC, cout, grad_out, cout, weights, cout, w.dwf, KC, inv_n, nullptr, nullptr, 0, 0.f, 0, nullptr};
@@ -244,6 +260,44 @@ extern "C" int d3f_kpconv_backward_ex(const float* q_pts, const float* s_pts, co
                nq, ns, H, K, cin, kp_extent, influence, aggregation, idx_is_64 ? 1 : 0, deformed ? 1 : 0};
     return kp2_scatter_launch(a2, w.dwf, wf_unmod, grad_x, deformed ? grad_kernel_points : nullptr,
                               deformed ? grad_modulations : nullptr, stream);
+}
+
+// The two halves of the list-based backward as separate entry points, so that a caller can run the weight-gradient and
+// the data-gradient GEMM concurrently on two streams once G is there (blocks._KPConvFunction.backward does).
+extern "C" int d3f_kpconv_gather_transposed(const float* q_pts, const float* s_pts, const int32_t* t_offsets,
+                                            const int32_t* t_src, const float* grad_out, const float* inv_n,
+                                            const float* kernel_points, int nq, int ns, int K, int cout, float kp_extent,
+                                            int influence, int aggregation, float* G, d3f_stream stream) {
+    D3F_REQUIRE(nq >= 0 && ns >= 0 && K >= 1 && K <= 16 && cout >= 1, D3F_ERR_INVALID, "bad sizes");
+    D3F_REQUIRE(kp2t_supported(nq, cout), D3F_ERR_UNSUPPORTED, "Cout must be a multiple of 32 and Nq * Cout < 2^31");
+    D3F_REQUIRE(influence >= 0 && influence <= 2 && aggregation >= 0 && aggregation <= 1, D3F_ERR_INVALID, "bad mode");
+    if (ns == 0) return D3F_OK;
+    D3F_REQUIRE(q_pts && s_pts && t_offsets && t_src && grad_out && inv_n && kernel_points && G, D3F_ERR_INVALID, "null pointer");
+    Kp2tArgs ta{q_pts, s_pts, t_offsets, t_src, grad_out, inv_n, kernel_points, nq, ns, K, cout, kp_extent, influence, aggregation};
+    return kp2t_correlate_launch(ta, G, (cudaStream_t)stream);
+}
+
+extern "C" int d3f_kpconv_grads_from_gathered(const float* G, const float* x, const float* weights, int ns, int K, int cin,
+                                              int cout, float* grad_x, float* grad_weights, d3f_stream stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    D3F_REQUIRE(ns >= 0 && K >= 1 && cin >= 1 && cout >= 1 && (cout & 3) == 0, D3F_ERR_INVALID, "bad sizes");
+    if (ns == 0) {
+        if (grad_weights) D3F_CHECK_CUDA(cudaMemsetAsync(grad_weights, 0, sizeof(float) * (size_t)K * cin * cout, stream));
+        return D3F_OK;
+    }
+    D3F_REQUIRE(G && (!grad_weights || x) && (!grad_x || weights), D3F_ERR_INVALID, "null pointer");
+    if (grad_weights) {     // grad_W[k,c,o] = sum_j x[j,c] G[j,k,o]: C written in the [K, Cin, Cout] layout
+        D3fGemm g{cin, K * cout, ns, x, cin, G, K * cout, grad_weights, cout, nullptr, nullptr, nullptr, 0, 0.f, 0, nullptr,
+                  nullptr, nullptr, 0, 0, 0, cout, (long long)cin * cout};
+        const int rc = d3f_gemm_launch(g, true, false, stream);
+        if (rc) return rc;
+    }
+    if (grad_x) {           // grad_x[j,c] = sum_{k,o} G[j,k,o] W[k,c,o]: W addressed block-wise as B^T
+        D3fGemm g{ns, cin, K * cout, G, K * cout, weights, cout, grad_x, cin, nullptr, nullptr, nullptr, 0, 0.f, 0, nullptr,
+                  nullptr, nullptr, 0, cout, (long long)cin * cout};
+        return d3f_gemm_launch(g, false, true, stream);
+    }
+    return D3F_OK;
 }
 
 // 1 if d3f_kpconv_forward[_ex] runs this layer shape as ONE fused kernel (rigid, unmodulated, linear influence, sum

@@ -135,17 +135,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
-// shared memory (bytes): B tiles [2] | rec [FQ][HP] float4 | idx [FQ][HP] i32 | inv_n [4][SBQ] f32 | xch [2][32][SBQ+1] f32 |
-// out tile [SBQ][COUT] f32 | barriers
+// shared memory (bytes): B tiles [2] (16 kernel-point slots each: the 16th takes the lanes that own no kernel point, so the
+// stores need no predicate; the MMAs read K of them) | rec [FQ][HP] float4 | idx [2][FQ][HP] i32 | inv_n [4][SBQ] f32 |
+// xch [2][32][SBQ+1] f32 | out tile [SBQ][COUT] f32 | barriers
+constexpr int NG = 6, HP = NG * 8, NH = 2;      // neighbour columns are padded to 48 = 6 groups of 8 = 2 passes of 32 lanes
+constexpr int RING = 3;                         // feature-row loads kept in flight per lane: 3 groups (24 registers)
 struct FusedSmem {
     int b_bytes, rec_off, idx_off, invn_off, xch_off, out_off, bar_off, total;
 };
-__host__ __device__ inline FusedSmem fused_smem(int K, int HP) {
+__host__ __device__ inline FusedSmem fused_smem() {
     FusedSmem m;
-    m.b_bytes = (K * CIN / 8) * B_LBO;
+    m.b_bytes = (16 * CIN / 8) * B_LBO;
     m.rec_off = (2 * m.b_bytes + 127) & ~127;
     m.idx_off = m.rec_off + FQ * HP * 16;
-    m.invn_off = m.idx_off + FQ * HP * 4;
+    m.invn_off = m.idx_off + 2 * FQ * HP * 4;
     m.xch_off = m.invn_off + 4 * SBQ * 4;
     m.out_off = (m.xch_off + 2 * 32 * (SBQ + 1) * 4 + 127) & ~127;
     m.bar_off = m.out_off + SBQ * COUT * 4;
@@ -153,12 +156,11 @@ __host__ __device__ inline FusedSmem fused_smem(int K, int HP) {
     return m;
 }
 
-template <bool IDX64, int NG>     // NG = padded neighbour columns / 8
+template <bool IDX64>
 __global__ void __launch_bounds__(NT, 1)
 kpf_fused_kernel(FusedArgs a) {
-    constexpr int HP = NG * 8, NH = (HP + 31) / 32;
     extern __shared__ __align__(128) unsigned char smem[];
-    const FusedSmem L = fused_smem(a.K, HP);
+    const FusedSmem L = fused_smem();
     float4* rec_all = (float4*)(smem + L.rec_off);
     int* idx_all = (int*)(smem + L.idx_off);
     float* invn_s = (float*)(smem + L.invn_off);
@@ -205,7 +207,7 @@ kpf_fused_kernel(FusedArgs a) {
     if (warp < FQ) {
         // =========================================================================================== gather warps
         float4* rec = rec_all + (size_t)warp * HP;
-        int* idx_s = idx_all + (size_t)warp * HP;
+        int* idx_buf = idx_all + (size_t)warp * HP;                 // + FQ * HP for the other parity
         const int gq = lane >> 2, tq = lane & 3;
         // A fragment of the distance product: row kp = (kx, ky, kz, |k|^2, 1, 0, 0, 0); rows >= K are zero
         uint32_t kh[4], kl[4];
@@ -220,40 +222,52 @@ kpf_fused_kernel(FusedArgs a) {
             split_tf32(v, kh[i], kl[i]);
         }
         const float inv_ext = 1.0f / a.extent;
-        const float* __restrict__ x = a.x;
+        const float* __restrict__ xg = a.x + 4 * gq;
+        const int nq = a.nq, H = a.H, ns = a.ns;
+        const long long ld = a.ld;
+        const int q_first = r_start * FQ + warp;                    // this warp's queries: q_first + 16 j
         bool ok = true;
 
-        // ---- pipeline stages (see the header): S0 index row -> registers
-        auto load_idx = [&](int qi, int (&id)[NH]) {
+        // ---- pipeline stages (see the header).  S0: index row -> registers, RAW (validated one iteration later, when it is
+        // consumed: checking it here would wait for the load that was just issued); the low word is kept for 64-bit
+        // indices together with a "high word is zero" flag folded into bit 31
+        auto load_idx = [&](int j, int (&id)[NH]) {
+            const int qi = q_first + FQ * j;
+            const bool live = j < my_rounds && qi < nq;
 #pragma unroll
             for (int t = 0; t < NH; ++t) {
                 const int h = 32 * t + lane;
-                long long v = -1;
-                if (qi < a.nq && h < a.H)
-                    v = IDX64 ? __ldg((const long long*)a.inds + (size_t)qi * a.ld + h)
-                              : (long long)__ldg((const int*)a.inds + (size_t)qi * a.ld + h);
-                id[t] = (v >= 0 && v < a.ns) ? (int)v : -1;
+                int v = -1;
+                if (live && h < H) {
+                    if (IDX64) {
+                        const int2 w = __ldg((const int2*)a.inds + (size_t)qi * ld + h);
+                        v = w.x | (w.y ? 0x80000000 : 0);             // any high bits -> negative -> shadow
+                    } else {
+                        v = __ldg((const int*)a.inds + (size_t)qi * ld + h);
+                    }
+                }
+                id[t] = v;
             }
         };
         // S1a: support points / flags of the indexed neighbours -> registers; index row -> shared memory; group count
-        auto load_pts = [&](int qi, const int (&id)[NH], float (&sx)[NH], float (&sy)[NH], float (&sz)[NH], int (&rp)[NH],
-                            float (&qv)[3]) -> int {
+        auto load_pts = [&](int j, int (&id)[NH], float (&sx)[NH], float (&sy)[NH], float (&sz)[NH], int (&rp)[NH],
+                            float (&qv)[3], int* idx_s) -> int {
+            const int qi = q_first + FQ * j;
             int hend = 0;
 #pragma unroll
             for (int t = 0; t < NH; ++t) {
                 const int h = 32 * t + lane;
-                const bool valid = id[t] >= 0;
-                sx[t] = sy[t] = sz[t] = 0.f; rp[t] = 0;
-                if (valid) {
-                    sx[t] = __ldg(a.s + 3 * (size_t)id[t]); sy[t] = __ldg(a.s + 3 * (size_t)id[t] + 1); sz[t] = __ldg(a.s + 3 * (size_t)id[t] + 2);
-                    rp[t] = __ldg(a.rowpos + id[t]);
-                }
-                if (h < HP) idx_s[h] = valid ? id[t] : 0;
-                const unsigned bv = __ballot_sync(FULL, valid);
+                if ((unsigned)id[t] >= (unsigned)ns) id[t] = -1;    // shadow index (= Ns), padding, garbage: no neighbour
+                const int i = max(id[t], 0);                        // shadow rows read point 0 and are masked below
+                const float* sp = a.s + 3 * (size_t)i;
+                sx[t] = __ldg(sp); sy[t] = __ldg(sp + 1); sz[t] = __ldg(sp + 2);
+                rp[t] = __ldg(a.rowpos + i);
+                if (h < HP) idx_s[h] = i;
+                const unsigned bv = __ballot_sync(FULL, id[t] >= 0);
                 if (bv) hend = 32 * t + 32 - __clz(bv);
             }
-            qv[0] = qv[1] = qv[2] = 0.f;
-            if (qi < a.nq) { qv[0] = __ldg(a.q + 3 * (size_t)qi); qv[1] = __ldg(a.q + 3 * (size_t)qi + 1); qv[2] = __ldg(a.q + 3 * (size_t)qi + 2); }
+            const float* qp = a.q + 3 * (size_t)min(qi, nq - 1);
+            qv[0] = __ldg(qp); qv[1] = __ldg(qp + 1); qv[2] = __ldg(qp + 2);
             return (hend + 7) >> 3;
         };
         // S1b: records (-2r, |r|^2) -> shared memory, density count
@@ -264,45 +278,44 @@ kpf_fused_kernel(FusedArgs a) {
             for (int t = 0; t < NH; ++t) {
                 const int h = 32 * t + lane;
                 const bool valid = id[t] >= 0;
-                float4 r = make_float4(0.f, 0.f, 0.f, 1e30f);                  // shadow / padding: w = 0
-                if (valid) {
-                    const float rx = sx[t] - qv[0], ry = sy[t] - qv[1], rz = sz[t] - qv[2];
-                    r = make_float4(-2.0f * rx, -2.0f * ry, -2.0f * rz, rx * rx + ry * ry + rz * rz);
-                }
+                const float rx = sx[t] - qv[0], ry = sy[t] - qv[1], rz = sz[t] - qv[2];
+                float4 r = make_float4(-2.0f * rx, -2.0f * ry, -2.0f * rz, rx * rx + ry * ry + rz * rz);
+                if (!valid) r = make_float4(0.f, 0.f, 0.f, 1e30f);             // shadow / padding: w = 0
                 if (h < HP) rec[h] = r;
                 count += __popc(__ballot_sync(FULL, valid && rp[t] != 0));
             }
             return count;
         };
-        auto load_x = [&](int g, float4& xa, float4& xb) {
+        auto load_x = [&](const int* idx_s, int g, float4& xa, float4& xb) {
             const int2 id = *(const int2*)&idx_s[8 * g + 2 * tq];              // neighbours 2tq, 2tq+1 of the group
-            xa = __ldg((const float4*)(x + (unsigned)id.x * (unsigned)CIN + 4 * gq));
-            xb = __ldg((const float4*)(x + (unsigned)id.y * (unsigned)CIN + 4 * gq));
+            xa = __ldg((const float4*)(xg + (unsigned)id.x * (unsigned)CIN));
+            xb = __ldg((const float4*)(xg + (unsigned)id.y * (unsigned)CIN));
         };
-        auto q_of = [&](int j) { return j < my_rounds ? (r_start + j) * FQ + warp : a.nq; };
 
-        // ---- prologue: query 0 completely staged, index row of query 1 in flight
+        // ---- prologue: query 0 completely staged, its first RING groups of rows and the index row of query 1 in flight
         int nid[NH], nid2[NH];
         float sx[NH], sy[NH], sz[NH], qv[3];
         int rp[NH];
-        float4 xa[NG], xb[NG];
-        load_idx(q_of(0), nid);
-        int ng = load_pts(q_of(0), nid, sx, sy, sz, rp, qv);
+        float4 xa[RING], xb[RING];
+        load_idx(0, nid);
+        int ng = load_pts(0, nid, sx, sy, sz, rp, qv, idx_buf);
         int count = store_rec(nid, sx, sy, sz, rp, qv);
         __syncwarp();
 #pragma unroll
-        for (int g = 0; g < NG; ++g)
-            if (g < ng) load_x(g, xa[g], xb[g]);
-        load_idx(q_of(1), nid);
+        for (int g = 0; g < RING; ++g)
+            if (g < ng) load_x(idx_buf, g, xa[g], xb[g]);
+        load_idx(1, nid);
 
         for (int j = 0; j < my_rounds; ++j) {
-            const int qi = q_of(j);
-            const bool qvalid = qi < a.nq;
+            const int qi = q_first + FQ * j;
+            const bool qvalid = qi < nq;
+            const int* idx_cur = idx_buf + (j & 1) * (FQ * HP);
+            int* idx_nxt = idx_buf + ((j + 1) & 1) * (FQ * HP);
             // ---- stage the next queries: points of j+1 (its index row arrived during query j-1), index row of j+2
-            __syncwarp();                                   // every lane has issued its feature loads from idx_s (query j)
-            const int ng_next = load_pts(q_of(j + 1), nid, sx, sy, sz, rp, qv);
-            load_idx(q_of(j + 2), nid2);
-            __syncwarp();                                   // idx_s (query j+1) visible
+            __syncwarp();                                   // idx_nxt held query j-1's row: every lane is done with it
+            const int ng_next = load_pts(j + 1, nid, sx, sy, sz, rp, qv, idx_nxt);
+            load_idx(j + 2, nid2);
+            __syncwarp();                                   // idx_nxt visible to the feature-row loads below
 
             float acc[4][4];
 #pragma unroll
@@ -314,7 +327,7 @@ kpf_fused_kernel(FusedArgs a) {
                 if (g < ng) {
                     // ---- B: sq[kp, neighbour] for the group's 8 neighbours, then the influences
                     const float rv = ((const float*)rec)[(8 * g + gq) * 4 + tq];      // B[k = tq][n = gq], k = 3 is the constant 1
-                    const float r2 = __shfl_sync(FULL, rv, lane | 3);                 // |r|^2 of neighbour gq
+                    const float r2 = ((const float*)rec)[(8 * g + gq) * 4 + 3];       // |r|^2 of neighbour gq (broadcast read)
                     uint32_t bh[2], bl[2];
                     split_tf32(tq == 3 ? 1.0f : rv, bh[0], bl[0]);
                     split_tf32(tq == 0 ? r2 : 0.f, bh[1], bl[1]);                     // B[k = tq + 4][n = gq]
@@ -325,7 +338,7 @@ kpf_fused_kernel(FusedArgs a) {
                     // C fragment: c0 (kp gq, nb 2tq) c1 (gq, 2tq+1) c2 (gq+8, 2tq) c3 (gq+8, 2tq+1)
                     float w[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) w[i] = fmaxf(1.0f - fast_sqrt(fmaxf(sq[i], 0.f)) * inv_ext, 0.f);
+                    for (int i = 0; i < 4; ++i) w[i] = fmaxf(fmaf(-fast_sqrt(fmaxf(sq[i], 0.f)), inv_ext, 1.0f), 0.f);
                     // A fragment of the correlation: a0 (kp gq, col tq) a1 (gq+8, tq) a2 (gq, tq+4) a3 (gq+8, tq+4) with
                     // column tq <-> neighbour 2tq and column tq+4 <-> neighbour 2tq+1 of the group
                     uint32_t ah[4], al[4];
@@ -333,8 +346,8 @@ kpf_fused_kernel(FusedArgs a) {
                     split_tf32(w[2], ah[1], al[1]);
                     split_tf32(w[1], ah[2], al[2]);
                     split_tf32(w[3], ah[3], al[3]);
-                    const float va[4] = {xa[g].x, xa[g].y, xa[g].z, xa[g].w};
-                    const float vb[4] = {xb[g].x, xb[g].y, xb[g].z, xb[g].w};
+                    const float va[4] = {xa[g % RING].x, xa[g % RING].y, xa[g % RING].z, xa[g % RING].w};
+                    const float vb[4] = {xb[g % RING].x, xb[g % RING].y, xb[g % RING].z, xb[g % RING].w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {          // n-tile e holds channels 4n + e, n = 0..7
                         uint32_t xh[2], xl[2];
@@ -345,7 +358,12 @@ kpf_fused_kernel(FusedArgs a) {
                         mma_tf32(acc[e], ah, xh);
                     }
                 }
-                if (g < ng_next) load_x(g, xa[g], xb[g]);   // the freed registers take query j+1's rows of this group
+                // the freed ring slot takes the rows RING groups ahead: of this query, or of the next one
+                if (g + RING < NG) {
+                    if (g + RING < ng) load_x(idx_cur, g + RING, xa[g % RING], xb[g % RING]);
+                } else {
+                    if (g + RING - NG < ng_next) load_x(idx_nxt, g + RING - NG, xa[g % RING], xb[g % RING]);
+                }
             }
             // ---- records of query j+1 (its support points have arrived by now)
             __syncwarp();                                   // all lanes are done reading rec (query j)
@@ -369,23 +387,28 @@ kpf_fused_kernel(FusedArgs a) {
             const int sb = j >> 1, slot = (j & 1) * FQ + warp;
             if ((j & 1) == 0 && sb >= 2) ok &= mbar_wait(bar_done + 8 * (sb & 1), ((sb >> 1) - 1) & 1);   // MMAs of sb-2 have read it
             if (j == 2) ok &= mbar_wait(bar_wfree, 0);                      // the second tile was the staging area of W
-            // (those were issued after the epilogue of super-batch sb-3, and sb-4 used this inv_n slot: safe to overwrite)
+            // (those MMAs were issued after the epilogue of super-batch sb-3, and sb-4 used this inv_n slot: safe to overwrite)
             if (lane == 0) invn_s[(sb & 3) * SBQ + slot] = invn;
             {
                 unsigned char* tile = smem + (size_t)(sb & 1) * L.b_bytes + (slot >> 3) * B_SBO + (slot & 7) * 16;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
-                    const int k = gq + 8 * half;
-                    if (k < a.K) {
-                        // channels 8tq .. 8tq+7 of kernel point k = ONE 16-byte K unit: kc = 32 k + 8 tq
-                        uint32_t t1[8], t2[8], t3[8];
+                    // channels 8tq .. 8tq+7 of kernel point k = gq + 8 half = ONE 16-byte K unit (kc = 32 k + 8 tq); v = b1 + b2 +
+                    // b3 with bf16 terms: packing the HIGH halves of two fp32 words truncates them to bf16
+                    float v[8], r[8];
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) split_bf16x3(acc[c & 3][2 * half + (c >> 2)], t1[c], t2[c], t3[c]);
-                        unsigned char* p = tile + (size_t)(k * (CIN / 8) + tq) * B_LBO;
-                        *(uint4*)p = make_uint4(pack_bf16(t1[0], t1[1]), pack_bf16(t1[2], t1[3]), pack_bf16(t1[4], t1[5]), pack_bf16(t1[6], t1[7]));
-                        *(uint4*)(p + 4 * B_SBO) = make_uint4(pack_bf16(t2[0], t2[1]), pack_bf16(t2[2], t2[3]), pack_bf16(t2[4], t2[5]), pack_bf16(t2[6], t2[7]));
-                        *(uint4*)(p + 8 * B_SBO) = make_uint4(pack_bf16(t3[0], t3[1]), pack_bf16(t3[2], t3[3]), pack_bf16(t3[4], t3[5]), pack_bf16(t3[6], t3[7]));
-                    }
+                    for (int c = 0; c < 8; ++c) v[c] = acc[c & 3][2 * half + (c >> 2)];
+                    unsigned char* p = tile + (size_t)((gq + 8 * half) * (CIN / 8) + tq) * B_LBO;
+                    *(uint4*)p = make_uint4(pack_bf16(__float_as_uint(v[0]), __float_as_uint(v[1])), pack_bf16(__float_as_uint(v[2]), __float_as_uint(v[3])),
+                                            pack_bf16(__float_as_uint(v[4]), __float_as_uint(v[5])), pack_bf16(__float_as_uint(v[6]), __float_as_uint(v[7])));
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) r[c] = v[c] - __uint_as_float(__float_as_uint(v[c]) & BF16_MASK);
+                    *(uint4*)(p + 4 * B_SBO) = make_uint4(pack_bf16(__float_as_uint(r[0]), __float_as_uint(r[1])), pack_bf16(__float_as_uint(r[2]), __float_as_uint(r[3])),
+                                                          pack_bf16(__float_as_uint(r[4]), __float_as_uint(r[5])), pack_bf16(__float_as_uint(r[6]), __float_as_uint(r[7])));
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) r[c] = r[c] - __uint_as_float(__float_as_uint(r[c]) & BF16_MASK);
+                    *(uint4*)(p + 8 * B_SBO) = make_uint4(pack_bf16(__float_as_uint(r[0]), __float_as_uint(r[1])), pack_bf16(__float_as_uint(r[2]), __float_as_uint(r[3])),
+                                                          pack_bf16(__float_as_uint(r[4]), __float_as_uint(r[5])), pack_bf16(__float_as_uint(r[6]), __float_as_uint(r[7])));
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");      // generic-proxy stores -> async proxy (UMMA)
@@ -501,28 +524,15 @@ kpf_fused_kernel(FusedArgs a) {
 }
 
 template <bool IDX64>
-int fused_launch_ng(const FusedArgs& a, int HP, int grid, cudaStream_t stream) {
-    const FusedSmem L = fused_smem(a.K, HP);
-#define KPF_GO(NG_)                                                                                               \
-    do {                                                                                                          \
-        auto kern = kpf_fused_kernel<IDX64, NG_>;                                                                 \
-        static bool attr_set = false;                                                                             \
-        if (!attr_set) {                                                                                          \
-            D3F_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));  \
-            attr_set = true;                                                                                      \
-        }                                                                                                         \
-        kern<<<grid, NT, L.total, stream>>>(a);                                                                   \
-    } while (0)
-    switch (HP / 8) {
-        case 1: KPF_GO(1); break;
-        case 2: KPF_GO(2); break;
-        case 3: KPF_GO(3); break;
-        case 4: KPF_GO(4); break;
-        case 5: KPF_GO(5); break;
-        case 6: KPF_GO(6); break;
-        default: d3f_set_error("kpf_fused: unsupported neighbour count"); return D3F_ERR_UNSUPPORTED;
+int fused_launch(const FusedArgs& a, int grid, cudaStream_t stream) {
+    const FusedSmem L = fused_smem();
+    auto kern = kpf_fused_kernel<IDX64>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        D3F_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        attr_set = true;
     }
-#undef KPF_GO
+    kern<<<grid, NT, L.total, stream>>>(a);
     D3F_CHECK_LAUNCH();
     return D3F_OK;
 }
@@ -532,7 +542,7 @@ int fused_launch_ng(const FusedArgs& a, int HP, int grid, cudaStream_t stream) {
 // rigid, unmodulated, linear influence, sum aggregation, Cin = Cout = 32, K <= 15 (W^T as bf16 x 3 takes 16 K of the 512
 // tensor-memory columns, D 96 more), <= 48 neighbour columns (all of a query's row loads are kept in flight in registers)
 bool kpf_fused_eligible(int H, int K, int cin, int cout) {
-    return cin == CIN && cout == COUT && K >= 1 && K <= 15 && H >= 1 && H <= 48;
+    return cin == CIN && cout == COUT && K >= 1 && K <= 15 && H >= 1 && H <= HP;
 }
 
 int kpf_fused_launch(const Kp2Args& g, const float* weights, const float* bias, int act, float slope, float* out,
@@ -543,10 +553,9 @@ int kpf_fused_launch(const Kp2Args& g, const float* weights, const float* bias, 
         D3F_CHECK_CUDA(cudaGetDevice(&dev));
         D3F_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
-    const int HP = (g.H + 7) & ~7;
     const int n_rounds = (g.nq + FQ - 1) / FQ;
     const int grid = n_rounds < n_sm ? n_rounds : n_sm;   // persistent: one CTA per SM (it owns all 512 tensor-memory columns)
     FusedArgs a{g.q, g.s, g.inds, g.ld, g.x, g.rowpos, g.kp, weights, bias, out, inv_n, wf,
                 g.nq, g.ns, g.H, g.K, g.extent, act, slope, d3f_fail_flag_device()};
-    return g.idx64 ? fused_launch_ng<true>(a, HP, grid, stream) : fused_launch_ng<false>(a, HP, grid, stream);
+    return g.idx64 ? fused_launch<true>(a, grid, stream) : fused_launch<false>(a, grid, stream);
 }

@@ -262,6 +262,34 @@ def kpconv_backward(q_pts, s_pts, inds, x, weights, kernel_points, extent, influ
     return gx, gw, gkp, gmod
 
 
+def kpconv_gather_transposed(q_pts, s_pts, transpose, grad_out, inv_n, kernel_points, cout, extent, influence, aggregation):
+    """G [Ns, K, Cout]: the forward gather over the transposed neighbour lists, reading rows of grad_out * (1/n)."""
+    lib = _lib.load()
+    t_off, t_src = transpose
+    nq, ns, K = q_pts.shape[0], s_pts.shape[0], kernel_points.shape[0]
+    grad_out = _cuda_f32(grad_out, "grad_out")
+    G = torch.empty((ns, K, cout), dtype=torch.float32, device=grad_out.device)
+    global launch_count
+    launch_count += 1
+    with _Timed(("kpconv_bwd_gather", nq, ns, cout)):
+        _lib.check(lib.d3f_kpconv_gather_transposed(_p(q_pts), _p(s_pts), _p(t_off), _p(t_src), _p(grad_out), _p(inv_n),
+                                                    _p(kernel_points), nq, ns, K, cout, float(extent), INFLUENCE[influence],
+                                                    AGGREGATION[aggregation], _p(G), _stream()))
+    return G
+
+
+def kpconv_grads_from_gathered(G, x, weights, need_x, need_w, gw_out=None):
+    """(grad_x [Ns, Cin] = G W^T, grad_weights [K, Cin, Cout] = x^T G) from the gathered gradient G."""
+    lib = _lib.load()
+    ns, K, cout = G.shape
+    cin = weights.shape[1]
+    gx = torch.empty((ns, cin), dtype=torch.float32, device=G.device) if need_x else None
+    gw = (gw_out if gw_out is not None else torch.empty_like(weights)) if need_w else None
+    with _Timed(("kpconv_bwd_gemm", ns, cin, cout, bool(need_x), bool(need_w))):
+        _lib.check(lib.d3f_kpconv_grads_from_gathered(_p(G), _p(x), _p(weights), ns, K, cin, cout, _p(gx), _p(gw), _stream()))
+    return gx, gw
+
+
 # --------------------------------------------------------------------------- descriptor distance / losses
 def pair_dist(a, b, metric="euclidean"):
     lib = _lib.load()

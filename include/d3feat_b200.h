@@ -107,7 +107,10 @@ int d3f_grid_subsample(const float* points, const int32_t* lengths, int n_batch,
  *
  * forward outputs:
  *   out [Nq,Cout]; wf [Nq,K,Cin] = kernel-point-weighted neighbour features after modulation
- *   (the [n_points,n_kpoints,in_fdim] tensor of blocks.py:362-366; saved for backward);
+ *   (the [n_points,n_kpoints,in_fdim] tensor of blocks.py:362-366; saved for backward).  wf may be NULL for rigid,
+ *   unmodulated, linear-influence, sum-aggregation layers with Cin = Cout = 32, K <= 15 and <= 48 neighbour columns:
+ *   those run as ONE fused kernel (gather + correlation + tcgen05 contraction, csrc/kpconv_fused.cu) that never
+ *   materialises wf; their backward then uses the transposed lists (d3f_kpconv_backward_ex);
  *   wf_unmod [Nq,K,Cin] or NULL (required iff modulations != NULL: wf before modulation);
  *   inv_n [Nq] = 1 / max(1, #neighbours with positive feature sum) (blocks.py:377-380);
  *   min_d2 [Nq,K] or NULL (deformed only, blocks.py:303).
@@ -170,6 +173,20 @@ int d3f_kpconv_backward_ex(const float* q_pts, const float* s_pts, const void* i
                            float* grad_modulations,
                            const int32_t* t_offsets, const int32_t* t_src,
                            void* workspace, size_t workspace_bytes, d3f_stream stream);
+
+/* The list-based backward of a rigid layer in two steps (what d3f_kpconv_backward_ex does internally when the lists are
+ * given), exposed so that the two GEMMs of step 2 can run concurrently on different streams:
+ *   1. G [Ns, K, Cout] = sum over the queries i that list support j of  w(i,k,j) * inv_n[i] * grad_out[i, :]
+ *      (the forward gather over the TRANSPOSED lists, reading rows of grad_out; Cout % 32 == 0);
+ *   2. grad_x [Ns, Cin] = G x W^T  and / or  grad_weights [K, Cin, Cout] = x^T G   (either may be NULL).
+ * Neither step needs the forward's kernel-point-weighted features wf: a training forward of such a layer may pass
+ * wf = NULL to d3f_kpconv_forward_ex. */
+int d3f_kpconv_gather_transposed(const float* q_pts, const float* s_pts, const int32_t* t_offsets, const int32_t* t_src,
+                                 const float* grad_out, const float* inv_n, const float* kernel_points,
+                                 int n_queries, int n_supports, int K, int c_out, float kp_extent, int influence,
+                                 int aggregation, float* G, d3f_stream stream);
+int d3f_kpconv_grads_from_gathered(const float* G, const float* x, const float* weights, int n_supports, int K, int c_in,
+                                   int c_out, float* grad_x, float* grad_weights, d3f_stream stream);
 
 /* ------------------------------------------------------------------------------------------
  * Pairwise descriptor distance + descriptor loss + detector loss.  Replaces cdist,
