@@ -40,7 +40,7 @@ SIGNATURES = {
                                      c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_i,
                                      c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
     "d3f_kpconv_gather_transposed": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_i, c_i, c_p, c_p]),
-    "d3f_kpconv_grads_from_gathered": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
+    "d3f_kpconv_grads_from_gathered": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_p]),
     "d3f_neighbors_transpose_workspace_bytes": (c_sz, [c_i]),
     "d3f_neighbors_transpose": (c_i, [c_p, c_i, c_i64, c_i, c_i, c_i, c_p, c_p, c_p, c_sz, c_p]),
     "d3f_set_kpconv_impl": (None, [c_i]),
@@ -65,7 +65,10 @@ SIGNATURES = {
                                     c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_i, c_p, c_i, c_f,
                                     c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
     "d3f_gemm_status_snapshot": (c_i, [c_p, c_p]),
-    "d3f_sgd_step": (c_i, [c_p, c_p, c_p, c_sz, c_p, c_f, c_f, c_p, c_i, c_p]),
+    "d3f_sgd_step": (c_i, [c_p, c_p, c_p, c_sz, c_p, c_f, c_f, c_p, c_i, c_i, c_p]),
+    "d3f_gemm_prezeroed": (c_i, [c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_i, c_f, c_p]),
+    "d3f_colsum_prezeroed": (c_i, [c_p, c_i, c_i, c_p, c_p]),
+    "d3f_leaky_backward_colsum_prezeroed": (c_i, [c_p, c_p, c_f, c_i, c_i, c_p, c_p, c_p]),
     "d3f_mutual_nn": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
     "d3f_pair_loss_aux_floats": (c_sz, [c_i]),
     "d3f_pair_dist": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),

@@ -208,8 +208,9 @@ tc_gemm_kernel(D3fGemm g) {
                     const int n = n0 + wn + ni * 8 + 2 * tq + e;
                     if (n >= g.N) continue;
                     float v = acc[mi][ni][half * 2 + e] * sc;
-                    float* dst = g.cblk ? g.C + (size_t)(n / g.cblk) * g.cblk_stride + (size_t)m * g.ldc + (n % g.cblk)
-                                        : g.C + (size_t)m * g.ldc + n;
+                    float* dst = g.ctrans ? g.C + (size_t)(m / g.cblk) * g.cblk_stride + (size_t)n * g.ldc + (m % g.cblk)
+                                 : g.cblk ? g.C + (size_t)(n / g.cblk) * g.cblk_stride + (size_t)m * g.ldc + (n % g.cblk)
+                                          : g.C + (size_t)m * g.ldc + n;
                     if (atomic) { atomicAdd(dst, v); continue; }
                     if (g.bias) v += g.bias[n];
                     if (g.bias2) v += g.bias2[n];
@@ -270,8 +271,10 @@ int d3f_gemm_launch(const D3fGemm& in, bool ta, bool tb, cudaStream_t stream, fl
     const int tiles = d3f_ceil_div(g.M, BM) * d3f_ceil_div(g.N, BN);
     int splits = 1, kps;
     const bool plain = !g.bias && !g.act && !g.bias2 && !g.res;   // atomically combined partials cannot take an epilogue
-    D3F_REQUIRE(!g.cblk || (!det_ws && (g.cblk & 3) == 0 && g.N % g.cblk == 0 && g.K > 0), D3F_ERR_UNSUPPORTED,
-                "blocked C needs the plain (non-deterministic) path, cblk % 4 == 0 and N % cblk == 0");
+    D3F_REQUIRE(!g.cblk || (!det_ws && (g.cblk & 3) == 0 && (g.ctrans ? g.M : g.N) % g.cblk == 0 && g.K > 0 && !g.bias &&
+                            !g.act && !g.bias2 && !g.res && !g.rs),
+                D3F_ERR_UNSUPPORTED, "blocked C needs the plain path without epilogue, cblk % 4 == 0 and a whole number of blocks");
+    D3F_REQUIRE(!g.ctrans || g.cblk, D3F_ERR_INVALID, "ctrans needs cblk");
     if (det_ws) {
         splits = det_splits(g.M, g.K);
         kps = splits > 1 ? DET_KPS : d3f_ceil_div(g.K > 0 ? g.K : 1, BK) * BK;
@@ -287,8 +290,9 @@ int d3f_gemm_launch(const D3fGemm& in, bool ta, bool tb, cudaStream_t stream, fl
         }
         kps = d3f_ceil_div(d3f_ceil_div(g.K > 0 ? g.K : 1, splits), BK) * BK;
         splits = d3f_ceil_div(g.K > 0 ? g.K : 1, kps);
-        const size_t c_floats = g.cblk ? (size_t)(g.N / g.cblk) * g.cblk_stride : (size_t)g.M * g.ldc;
-        if (splits > 1) D3F_CHECK_CUDA(cudaMemsetAsync(g.C, 0, sizeof(float) * c_floats, stream));
+        const size_t c_floats = g.ctrans ? (size_t)(g.M / g.cblk) * g.cblk_stride
+                                : g.cblk ? (size_t)(g.N / g.cblk) * g.cblk_stride : (size_t)g.M * g.ldc;
+        if (splits > 1 && !g.c_zeroed) D3F_CHECK_CUDA(cudaMemsetAsync(g.C, 0, sizeof(float) * c_floats, stream));
     }
     g.k_per_split = kps;
     if (g.K == 0) {
@@ -345,13 +349,27 @@ extern "C" int d3f_gemm_ex(int trans_a, int trans_b, int M, int N, int K, const 
     return d3f_gemm_launch(g, trans_a != 0, trans_b != 0, (cudaStream_t)stream, need ? (float*)workspace : &dummy, need);
 }
 
-extern "C" int d3f_gemm(int trans_a, int trans_b, int M, int N, int K, const float* A, int lda, const float* B,
-                        int ldb, float* C, int ldc, const float* row_scale, const float* k_scale,
-                        const float* bias, int leaky_relu, float slope, d3f_stream stream) {
+static int gemm_plain(int trans_a, int trans_b, int M, int N, int K, const float* A, int lda, const float* B,
+                      int ldb, float* C, int ldc, const float* row_scale, const float* k_scale,
+                      const float* bias, int leaky_relu, float slope, int c_zeroed, d3f_stream stream) {
     D3F_REQUIRE(M >= 0 && N >= 0 && K >= 0, D3F_ERR_INVALID, "bad sizes");
     if (M == 0 || N == 0) return D3F_OK;
     D3F_REQUIRE(C && (K == 0 || (A && B)), D3F_ERR_INVALID, "null pointer");
     D3F_REQUIRE(!(k_scale && trans_b), D3F_ERR_UNSUPPORTED, "k_scale is applied on B[k][n] loads only");
     D3fGemm g{M, N, K, A, lda, B, ldb, C, ldc, row_scale, k_scale, bias, leaky_relu, slope, 0, nullptr};
+    g.c_zeroed = c_zeroed && K > 0;
     return d3f_gemm_launch(g, trans_a != 0, trans_b != 0, (cudaStream_t)stream);
+}
+
+extern "C" int d3f_gemm(int trans_a, int trans_b, int M, int N, int K, const float* A, int lda, const float* B,
+                        int ldb, float* C, int ldc, const float* row_scale, const float* k_scale,
+                        const float* bias, int leaky_relu, float slope, d3f_stream stream) {
+    return gemm_plain(trans_a, trans_b, M, N, K, A, lda, B, ldb, C, ldc, row_scale, k_scale, bias, leaky_relu, slope, 0, stream);
+}
+
+// d3f_gemm for a C that the caller has already cleared (a slice of a gradient buffer zeroed once per step)
+extern "C" int d3f_gemm_prezeroed(int trans_a, int trans_b, int M, int N, int K, const float* A, int lda, const float* B,
+                                  int ldb, float* C, int ldc, const float* row_scale, const float* k_scale,
+                                  const float* bias, int leaky_relu, float slope, d3f_stream stream) {
+    return gemm_plain(trans_a, trans_b, M, N, K, A, lda, B, ldb, C, ldc, row_scale, k_scale, bias, leaky_relu, slope, 1, stream);
 }

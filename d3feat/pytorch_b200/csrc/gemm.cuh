@@ -25,6 +25,13 @@ struct D3fGemm {
     // cblk a multiple of 4).  KPConv's weight gradient from the transposed gather, dW[k][c][o] = sum_j x[j][c] G[j][k*Cout+o],
     // lands in the [K_pts, Cin, Cout] layout of the weights this way (cblk = Cout, cblk_stride = Cin*Cout, ldc = Cout).
     int cblk; long long cblk_stride;
+    // ctrans (with cblk): the blocks run along M and each block is stored transposed: element (m, n) lives at
+    // C[(m / cblk) * cblk_stride + n * ldc + m % cblk] -- dW^T = G^T x ([K*Cout, Cin]: 480 useful rows per 128-row tile
+    // instead of 32) written straight into the [K_pts, Cin, Cout] weight layout.
+    int ctrans;
+    // the caller guarantees C is zero on entry (a gradient buffer cleared once per step): split-K partial sums are
+    // accumulated with atomics WITHOUT the library's own zero fill (one memset node less per GEMM in the step's graph)
+    int c_zeroed;
 };
 
 // C[M,N] = act(rs[m] * sum_k opA(m,k) * ks[k] * opB(k,n) + bias[n] + bias2[n] + res[m,n]);  ta: A stored [K,M];  tb: B stored [N,K]

@@ -295,6 +295,15 @@ tc5_gemm_kernel(D3fGemm g) {
                 continue;
             }
             const float sc = g.rs ? g.rs[row] : 1.0f;
+            if (g.ctrans) {      // transposed column blocks (see gemm.cuh): scalar, element stride ldc
+                float* dt = g.C + (size_t)(row / g.cblk) * g.cblk_stride + (size_t)n * g.ldc + (row % g.cblk);
+                for (int e = 0; e < 4; ++e)
+                    if (n + e < g.N) {
+                        if (atomic) atomicAdd(dt + (size_t)e * g.ldc, xs[e] * sc);
+                        else dt[(size_t)e * g.ldc] = xs[e] * sc;
+                    }
+                continue;
+            }
             float* dst = g.cblk ? g.C + (size_t)(n / g.cblk) * g.cblk_stride + (size_t)row * g.ldc + (n % g.cblk)
                                 : g.C + (size_t)row * g.ldc + n;
             if (atomic) {

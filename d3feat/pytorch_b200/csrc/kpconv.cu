@@ -225,8 +225,8 @@ extern "C" int d3f_kpconv_backward_ex(const float* q_pts, const float* s_pts, co
         rc = kp2t_correlate_launch(ta, G, stream);
         if (rc) return rc;
         if (grad_weights) {
-            D3fGemm g{cin, K * cout, ns, x, cin, G, K * cout, grad_weights, cout, nullptr, nullptr, nullptr, 0, 0.f, 0, nullptr,
-                      nullptr, nullptr, 0, 0, 0, cout, (long long)cin * cout};
+            D3fGemm g{K * cout, cin, ns, G, K * cout, x, cin, grad_weights, cout, nullptr, nullptr, nullptr, 0, 0.f, 0, nullptr,
+                      nullptr, nullptr, 0, 0, 0, cout, (long long)cin * cout, 1};
             rc = d3f_gemm_launch(g, true, false, stream);
             if (rc) return rc;
         }
@@ -278,17 +278,19 @@ extern "C" int d3f_kpconv_gather_transposed(const float* q_pts, const float* s_p
 }
 
 extern "C" int d3f_kpconv_grads_from_gathered(const float* G, const float* x, const float* weights, int ns, int K, int cin,
-                                              int cout, float* grad_x, float* grad_weights, d3f_stream stream_) {
+                                              int cout, float* grad_x, float* grad_weights, int grad_weights_prezeroed,
+                                              d3f_stream stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     D3F_REQUIRE(ns >= 0 && K >= 1 && cin >= 1 && cout >= 1 && (cout & 3) == 0, D3F_ERR_INVALID, "bad sizes");
     if (ns == 0) {
-        if (grad_weights) D3F_CHECK_CUDA(cudaMemsetAsync(grad_weights, 0, sizeof(float) * (size_t)K * cin * cout, stream));
+        if (grad_weights && !grad_weights_prezeroed)
+            D3F_CHECK_CUDA(cudaMemsetAsync(grad_weights, 0, sizeof(float) * (size_t)K * cin * cout, stream));
         return D3F_OK;
     }
     D3F_REQUIRE(G && (!grad_weights || x) && (!grad_x || weights), D3F_ERR_INVALID, "null pointer");
-    if (grad_weights) {     // grad_W[k,c,o] = sum_j x[j,c] G[j,k,o]: C written in the [K, Cin, Cout] layout
-        D3fGemm g{cin, K * cout, ns, x, cin, G, K * cout, grad_weights, cout, nullptr, nullptr, nullptr, 0, 0.f, 0, nullptr,
-                  nullptr, nullptr, 0, 0, 0, cout, (long long)cin * cout};
+    if (grad_weights) {     // grad_W^T = G^T x ([K*Cout, Cin]), every [Cout, Cin] block stored transposed: the [K, Cin, Cout] weight layout
+        D3fGemm g{K * cout, cin, ns, G, K * cout, x, cin, grad_weights, cout, nullptr, nullptr, nullptr, 0, 0.f, 0, nullptr,
+                  nullptr, nullptr, 0, 0, 0, cout, (long long)cin * cout, 1, grad_weights_prezeroed};
         const int rc = d3f_gemm_launch(g, true, false, stream);
         if (rc) return rc;
     }

@@ -340,7 +340,12 @@ kp2_scatter_kernel(Kp2Args a, int HP, const float* __restrict__ dwf, const float
         for (int k = 0; k < KP; ++k) { gkp[k][0] = gkp[k][1] = gkp[k][2] = 0.f; gmod[k] = 0.f; }
     }
 
-    for (int c0 = 0; c0 < cin; c0 += 32 * CG) {
+    // gridDim.y > 1: the channel chunks of a query are spread over blockIdx.y (few queries x many channels x wide
+    // neighbourhoods -- the deformable layers of levels 3-4 -- would otherwise run on a fraction of the SMs); the
+    // per-query outputs are then combined with atomics into zero-filled buffers
+    const bool split = gridDim.y > 1;
+    const int c_lo = split ? (int)blockIdx.y * 32 * CG : 0, c_hi = split ? min(cin, c_lo + 32 * CG) : cin;
+    for (int c0 = c_lo; c0 < c_hi; c0 += 32 * CG) {
         float d[CG][KP];   // m[k] * dwf[k, c]
 #pragma unroll
         for (int j = 0; j < CG; ++j) {
@@ -424,13 +429,19 @@ kp2_scatter_kernel(Kp2Args a, int HP, const float* __restrict__ dwf, const float
                 for (int ax = 0; ax < 3; ++ax) {
                     float v = gkp[k][ax];
                     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-                    if (lane == 0) grad_kp[((size_t)qi * a.K + k) * 3 + ax] = v;
+                    if (lane == 0) {
+                        if (split) atomicAdd(&grad_kp[((size_t)qi * a.K + k) * 3 + ax], v);
+                        else grad_kp[((size_t)qi * a.K + k) * 3 + ax] = v;
+                    }
                 }
             }
             if (grad_mod) {
                 float v = gmod[k];
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-                if (lane == 0) grad_mod[(size_t)qi * a.K + k] = v;
+                if (lane == 0) {
+                    if (split) atomicAdd(&grad_mod[(size_t)qi * a.K + k], v);
+                    else grad_mod[(size_t)qi * a.K + k] = v;
+                }
             }
         }
     }
@@ -652,12 +663,20 @@ template <bool IDX64, bool DEF>
 int scatter_cg(const Kp2Args& a, int HP, int grid, int warps, size_t smem, const float* dwf, const float* wf_unmod,
                float* grad_x, float* grad_kp, float* grad_mod, cudaStream_t stream) {
     const int cg = a.cin <= 32 ? 1 : (a.cin <= 64 ? 2 : 4);
+    // few CTAs and several 128-channel chunks: one chunk per blockIdx.y (see the kernel)
+    const int chunks = (a.cin + 32 * cg - 1) / (32 * cg);
+    const int gy = (chunks > 1 && grid < 2 * 148) ? chunks : 1;
+    if (gy > 1) {
+        if (grad_kp) D3F_CHECK_CUDA(cudaMemsetAsync(grad_kp, 0, sizeof(float) * (size_t)a.nq * a.K * 3, stream));
+        if (grad_mod) D3F_CHECK_CUDA(cudaMemsetAsync(grad_mod, 0, sizeof(float) * (size_t)a.nq * a.K, stream));
+    }
+    const dim3 grid2(grid, gy);
 #define KP2_GO(CG_)                                                                                       \
     do {                                                                                                  \
         auto kern = kp2_scatter_kernel<IDX64, DEF, CG_>;                                                  \
         int rc_ = kp2_set_smem(kern, smem);                                                               \
         if (rc_) return rc_;                                                                              \
-        kern<<<grid, warps * 32, smem, stream>>>(a, HP, dwf, wf_unmod, grad_x, grad_kp, grad_mod);        \
+        kern<<<grid2, warps * 32, smem, stream>>>(a, HP, dwf, wf_unmod, grad_x, grad_kp, grad_mod);       \
     } while (0)
     if (cg == 1) KP2_GO(1); else if (cg == 2) KP2_GO(2); else KP2_GO(4);
 #undef KP2_GO

@@ -30,14 +30,22 @@ sgd_scan_kernel(const float* __restrict__ g, size_t n, int32_t* __restrict__ fla
 // p, m updated in place;  g' = g + wd * p;  m = mu * m + g';  p -= lr * m      (torch.optim.SGD, dampening 0, no nesterov;
 // a zero-initialised momentum buffer reproduces torch's "first step: buf = g'")
 __global__ void __launch_bounds__(256)
-sgd_apply_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, size_t n,
-                 const float* __restrict__ lr_ptr, float mu, float wd, const int32_t* __restrict__ skip) {
-    if (skip && *skip) return;
-    const float lr = *lr_ptr;
+sgd_apply_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, size_t n,
+                 const float* __restrict__ lr_ptr, float mu, float wd, const int32_t* __restrict__ skip, int zero_grads) {
     const size_t n4 = n >> 2;
+    if (skip && *skip) {       // non-finite gradient: no update (trainer.py:104-111); the gradients are still consumed
+        if (zero_grads) {
+            for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+                ((float4*)g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (blockIdx.x == 0 && threadIdx.x < (n & 3)) g[(n4 << 2) + threadIdx.x] = 0.f;
+        }
+        return;
+    }
+    const float lr = *lr_ptr;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         float4 pv = ((float4*)p)[i], mv = ((float4*)m)[i];
-        const float4 gv = __ldg((const float4*)g + i);
+        const float4 gv = ((const float4*)g)[i];
+        if (zero_grads) ((float4*)g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         mv.x = mu * mv.x + (gv.x + wd * pv.x); mv.y = mu * mv.y + (gv.y + wd * pv.y);
         mv.z = mu * mv.z + (gv.z + wd * pv.z); mv.w = mu * mv.w + (gv.w + wd * pv.w);
         pv.x -= lr * mv.x; pv.y -= lr * mv.y; pv.z -= lr * mv.z; pv.w -= lr * mv.w;
@@ -49,6 +57,7 @@ sgd_apply_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
         const float mv = mu * m[i] + (g[i] + wd * p[i]);
         m[i] = mv;
         p[i] -= lr * mv;
+        if (zero_grads) g[i] = 0.f;
     }
 }
 
@@ -56,10 +65,12 @@ sgd_apply_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
 
 // params / grads / momentum: flat fp32 buffers of n elements (16-byte aligned); lr: device float; nonfinite_flag: device
 // int32 that is OR-ed with 1 when a gradient element is inf / nan (the caller clears it; when set the update is skipped,
-// exactly trainer.py:104-111).  check_finite = 0 skips the scan (flag is still honoured).
-extern "C" int d3f_sgd_step(float* params, const float* grads, float* momentum_buf, size_t n, const float* lr,
+// exactly trainer.py:104-111).  check_finite = 0 skips the scan (flag is still honoured).  zero_grads != 0 clears the
+// gradient buffer in the same pass (optimizer.zero_grad() of the next step: the backward kernels may then accumulate
+// into it without their own zero fills).
+extern "C" int d3f_sgd_step(float* params, float* grads, float* momentum_buf, size_t n, const float* lr,
                             float momentum, float weight_decay, int32_t* nonfinite_flag, int check_finite,
-                            d3f_stream stream_) {
+                            int zero_grads, d3f_stream stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n == 0) return D3F_OK;
     D3F_REQUIRE(params && grads && momentum_buf && lr, D3F_ERR_INVALID, "null pointer");
@@ -72,7 +83,8 @@ extern "C" int d3f_sgd_step(float* params, const float* grads, float* momentum_b
         sgd_scan_kernel<<<grid, 256, 0, stream>>>(grads, n, nonfinite_flag);
         D3F_CHECK_LAUNCH();
     }
-    sgd_apply_kernel<<<grid, 256, 0, stream>>>(params, grads, momentum_buf, n, lr, momentum, weight_decay, nonfinite_flag);
+    sgd_apply_kernel<<<grid, 256, 0, stream>>>(params, grads, momentum_buf, n, lr, momentum, weight_decay, nonfinite_flag,
+                                               zero_grads);
     D3F_CHECK_LAUNCH();
     return D3F_OK;
 }

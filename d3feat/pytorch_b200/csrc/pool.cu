@@ -325,10 +325,18 @@ static bool colsum_vec_geometry(int n_rows, int n_cols, dim3* grid, int* nv, int
 
 }  // namespace
 
-extern "C" int d3f_colsum(const float* x, int n_rows, int n_cols, float* out, d3f_stream stream_) {
+static int colsum_impl(const float* x, int n_rows, int n_cols, float* out, int prezeroed, d3f_stream stream_);
+extern "C" int d3f_colsum(const float* x, int n_rows, int n_cols, float* out, d3f_stream stream) {
+    return colsum_impl(x, n_rows, n_cols, out, 0, stream);
+}
+// `out` already cleared by the caller (gradient buffer zeroed once per step): no zero fill here
+extern "C" int d3f_colsum_prezeroed(const float* x, int n_rows, int n_cols, float* out, d3f_stream stream) {
+    return colsum_impl(x, n_rows, n_cols, out, 1, stream);
+}
+static int colsum_impl(const float* x, int n_rows, int n_cols, float* out, int prezeroed, d3f_stream stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     D3F_REQUIRE(n_rows >= 0 && n_cols >= 1 && out, D3F_ERR_INVALID, "bad arguments");
-    D3F_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * n_cols, stream));
+    if (!prezeroed) D3F_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * n_cols, stream));
     if (n_rows == 0) return D3F_OK;
     D3F_REQUIRE(x, D3F_ERR_INVALID, "null pointer");
     dim3 grid;
@@ -351,15 +359,25 @@ extern "C" int d3f_colsum(const float* x, int n_rows, int n_cols, float* out, d3
 // dz = grad * (y > 0 ? 1 : slope) and colsum[n] = sum_m dz[m, n] in one pass (y = the saved LeakyReLU OUTPUT).
 // Returns D3F_ERR_UNSUPPORTED for shapes the vector kernel does not take (n_cols must be 4 * 2^j, 16-byte aligned rows);
 // the caller then uses the two separate ops.
+static int leaky_colsum_impl(const float* grad, const float* y, float slope, int n_rows, int n_cols, float* dz,
+                             float* colsum, int prezeroed, d3f_stream stream_);
 extern "C" int d3f_leaky_backward_colsum(const float* grad, const float* y, float slope, int n_rows, int n_cols, float* dz,
-                                         float* colsum, d3f_stream stream_) {
+                                         float* colsum, d3f_stream stream) {
+    return leaky_colsum_impl(grad, y, slope, n_rows, n_cols, dz, colsum, 0, stream);
+}
+extern "C" int d3f_leaky_backward_colsum_prezeroed(const float* grad, const float* y, float slope, int n_rows, int n_cols,
+                                                   float* dz, float* colsum, d3f_stream stream) {
+    return leaky_colsum_impl(grad, y, slope, n_rows, n_cols, dz, colsum, 1, stream);
+}
+static int leaky_colsum_impl(const float* grad, const float* y, float slope, int n_rows, int n_cols, float* dz,
+                             float* colsum, int prezeroed, d3f_stream stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     D3F_REQUIRE(n_rows >= 0 && n_cols >= 1 && colsum, D3F_ERR_INVALID, "bad arguments");
     dim3 grid;
     int nv, nv_cta, rpc;
     if ((((size_t)grad | (size_t)y | (size_t)dz) & 15) != 0 || !colsum_vec_geometry(n_rows, n_cols, &grid, &nv, &nv_cta, &rpc))
         return D3F_ERR_UNSUPPORTED;
-    D3F_CHECK_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * n_cols, stream));
+    if (!prezeroed) D3F_CHECK_CUDA(cudaMemsetAsync(colsum, 0, sizeof(float) * n_cols, stream));
     if (n_rows == 0) return D3F_OK;
     D3F_REQUIRE(grad && y && dz, D3F_ERR_INVALID, "null pointer");
     colsum_vec_kernel<true><<<grid, 256, 0, stream>>>((const float4*)grad, n_rows, nv, nv_cta, rpc, colsum, (const float4*)y,

@@ -229,6 +229,8 @@ class PairStep:
     def _body_impl(self):
         cfg = self.config
         lib = _lib.load()
+        if self.flat_sgd is not None:
+            self.flat_sgd.zero_grad()     # one fill, while the main stream would otherwise wait for the first search
         batch, pyramid = collate_static(*self.inputs, cfg, self.limits, self.caps, self.lengths0, self.side_stream,
                                         transposes=self.optimizer is not None, search_stream=self.search_stream)
         feats, scores = self.model(batch)
@@ -247,10 +249,12 @@ class PairStep:
             if self.flat is not None:
                 self.flat.zero()
             else:
-                # FlatSGD(direct): every gradient is written in place by the kernel that computes it.  torch.optim:
-                # gradients are (re)created by the backward pass (inside a CUDA graph they come from the graph's private
-                # pool at the same addresses every replay).  Either way: no zero-fill, no accumulate kernel per parameter
-                self.optimizer.zero_grad(set_to_none=True)
+                # FlatSGD(direct): every gradient is written in place by the kernel that computes it (the flat buffer was
+                # cleared at the top of the step).  torch.optim: gradients are (re)created by the backward pass (inside a
+                # CUDA graph they come from the graph's private pool at the same addresses every replay).  Either way:
+                # no per-parameter zero-fill, no accumulate kernel per parameter
+                if self.flat_sgd is None:
+                    self.optimizer.zero_grad(set_to_none=True)
             loss.backward()
             if self.flat_sgd is not None:
                 self.flat_sgd.allreduce(self.group)

@@ -286,7 +286,8 @@ def kpconv_grads_from_gathered(G, x, weights, need_x, need_w, gw_out=None):
     gx = torch.empty((ns, cin), dtype=torch.float32, device=G.device) if need_x else None
     gw = (gw_out if gw_out is not None else torch.empty_like(weights)) if need_w else None
     with _Timed(("kpconv_bwd_gemm", ns, cin, cout, bool(need_x), bool(need_w))):
-        _lib.check(lib.d3f_kpconv_grads_from_gathered(_p(G), _p(x), _p(weights), ns, K, cin, cout, _p(gx), _p(gw), _stream()))
+        _lib.check(lib.d3f_kpconv_grads_from_gathered(_p(G), _p(x), _p(weights), ns, K, cin, cout, _p(gx), _p(gw),
+                                                      1 if (need_w and _prezeroed(gw_out)) else 0, _stream()))
     return gx, gw
 
 
@@ -499,10 +500,22 @@ def detection_scores(feats, neighbors, eval_mode):
 
 
 # --------------------------------------------------------------------------- tensor-core GEMM (3xTF32) + fused linear
+DST_SEEN = None   # optim.FlatSGD.verify_direct: set of id(param) whose gradient destination was handed to a kernel
+
+
 def grad_dst(param):
     """Destination a backward kernel writes the gradient of `param` into (optim.FlatSGD(direct=True) attaches a view of
     its flat gradient buffer), or None: the gradient is then returned to autograd as usual."""
-    return getattr(param, "_d3f_grad", None) if param is not None else None
+    dst = getattr(param, "_d3f_grad", None) if param is not None else None
+    if dst is not None and DST_SEEN is not None:
+        DST_SEEN.add(id(param))
+    return dst
+
+
+def _prezeroed(t):
+    """True for a destination inside a gradient buffer that its owner keeps cleared between steps (FlatSGD zeroes the
+    flat gradient in the optimiser kernel): kernels may accumulate into it without a zero fill of their own."""
+    return t is not None and getattr(t, "_d3f_prezeroed", False)
 
 
 def gemm(a, b, trans_a=False, trans_b=False, row_scale=None, k_scale=None, bias=None, slope=None, deterministic=False,
@@ -540,6 +553,8 @@ def gemm(a, b, trans_a=False, trans_b=False, row_scale=None, k_scale=None, bias=
             ws = _ws(lib.d3f_gemm_workspace_bytes(M, N, K), a.device)
             _lib.check(lib.d3f_gemm_ex(*head, _p(None if bias2 is None else _cuda_f32(bias2, "bias2")), _p(residual),
                                        N, *act, _p(ws), ws.numel(), _stream()))
+        elif _prezeroed(out):
+            _lib.check(lib.d3f_gemm_prezeroed(*head, *act, _stream()))
         else:
             _lib.check(lib.d3f_gemm(*head, *act, _stream()))
     return c
@@ -551,7 +566,8 @@ def colsum(x, out=None):
     x = _cuda_f32(x, "x")
     if out is None:
         out = torch.empty(x.shape[1], dtype=torch.float32, device=x.device)
-    _lib.check(lib.d3f_colsum(_p(x), x.shape[0], x.shape[1], _p(out), _stream()))
+    fn = lib.d3f_colsum_prezeroed if _prezeroed(out) else lib.d3f_colsum
+    _lib.check(fn(_p(x), x.shape[0], x.shape[1], _p(out), _stream()))
     return out
 
 
@@ -595,7 +611,8 @@ def leaky_backward_colsum(gy, y, slope, want_colsum=True, db_out=None):
     if want_colsum:
         dz = torch.empty_like(gy)
         db = db_out if db_out is not None else torch.empty(N, dtype=torch.float32, device=gy.device)
-        rc = lib.d3f_leaky_backward_colsum(_p(gy), _p(y), float(slope), M, N, _p(dz), _p(db), _stream())
+        fn = lib.d3f_leaky_backward_colsum_prezeroed if _prezeroed(db_out) else lib.d3f_leaky_backward_colsum
+        rc = fn(_p(gy), _p(y), float(slope), M, N, _p(dz), _p(db), _stream())
         if rc == 0:
             return dz, db
         if rc != -4:   # D3F_ERR_UNSUPPORTED: shape not covered by the vector kernel

@@ -59,6 +59,7 @@ class FlatSGD:
             g = self.flat_g[off:off + p.numel()].view_as(p)
             p.grad = g
             if direct:
+                g._d3f_prezeroed = True  # the optimiser kernel clears the flat gradient: kernels may accumulate into it
                 p._d3f_grad = g          # destination the backward kernels write into (ops.grad_dst)
         self.direct = direct
         self.lr = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
@@ -70,14 +71,17 @@ class FlatSGD:
 
     # -- torch.optim-like surface used by engine.PairStep
     def zero_grad(self, set_to_none=False):
-        if not self.direct:
-            self.flat_g.zero_()
+        """ONE fill of the flat gradient per step.  With direct=True that is what lets the backward kernels accumulate
+        split-K / row-block partial sums into their slices without ~100 per-kernel zero fills; engine.PairStep issues it
+        at the top of the step, where the main stream is idle waiting for the first radius search.  (Clearing the
+        gradient inside the optimiser kernel instead was measured 4.5x slower: 377 vs 84 us for 24.3 M parameters.)"""
+        self.flat_g.zero_()
 
     def step(self):
         lib = _lib.load()
         self.nonfinite.zero_()
         _lib.check(lib.d3f_sgd_step(_p(self.flat_p), _p(self.flat_g), _p(self.flat_m), self.n, _p(self.lr),
-                                    self.momentum, self.weight_decay, _p(self.nonfinite), 1,
+                                    self.momentum, self.weight_decay, _p(self.nonfinite), 1, 0,
                                     torch.cuda.current_stream().cuda_stream))
 
     def scheduler_step(self):
@@ -115,23 +119,20 @@ class FlatSGD:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=group)
 
     def verify_direct(self, run_step):
-        """Prove that one step overwrites EVERY gradient element (so no zero-fill is needed): poison, run, scan."""
-        self.flat_g.fill_(float("nan"))
-        pad = torch.ones(self.n, dtype=torch.bool, device=self.flat_g.device)
-        o = 0
-        for p in self.params:
-            pad[o:o + p.numel()] = False
-            o += (p.numel() + 3) // 4 * 4
-        self.flat_g[pad] = 0.0
-        run_step()
-        torch.cuda.synchronize()
-        bad = []
-        for n, p in zip(self.names, self.params):
-            if not bool(torch.isfinite(p.grad).all()):
-                bad.append(n)
-        if bad:
-            raise RuntimeError("FlatSGD(direct=True): these parameters did not receive a directly written gradient "
-                               "(or it is not finite): %s" % bad[:8])
+        """Prove that one step hands EVERY parameter's gradient slice to the kernel that computes it (so autograd never
+        accumulates into the flat buffer behind our back and nothing needs a per-parameter zero fill): record the
+        destinations fetched during `run_step()` (ops.grad_dst) and compare with the parameter list."""
+        from . import ops
+        ops.DST_SEEN = set()
+        try:
+            run_step()
+            torch.cuda.synchronize()
+            seen = ops.DST_SEEN
+        finally:
+            ops.DST_SEEN = None
+        missing = [n for n, p in zip(self.names, self.params) if id(p) not in seen]
+        if missing:
+            raise RuntimeError("FlatSGD(direct=True): no kernel took the gradient destination of %s" % missing[:8])
 
 
 EARLY_LEVEL = 3   # encoder blocks of pyramid levels >= 3 (and the whole decoder) form the first all-reduce bucket

@@ -180,13 +180,14 @@ int d3f_kpconv_backward_ex(const float* q_pts, const float* s_pts, const void* i
  *      (the forward gather over the TRANSPOSED lists, reading rows of grad_out; Cout % 32 == 0);
  *   2. grad_x [Ns, Cin] = G x W^T  and / or  grad_weights [K, Cin, Cout] = x^T G   (either may be NULL).
  * Neither step needs the forward's kernel-point-weighted features wf: a training forward of such a layer may pass
- * wf = NULL to d3f_kpconv_forward_ex. */
+ * wf = NULL to d3f_kpconv_forward_ex.  grad_weights_prezeroed != 0: the caller cleared grad_weights (see *_prezeroed). */
 int d3f_kpconv_gather_transposed(const float* q_pts, const float* s_pts, const int32_t* t_offsets, const int32_t* t_src,
                                  const float* grad_out, const float* inv_n, const float* kernel_points,
                                  int n_queries, int n_supports, int K, int c_out, float kp_extent, int influence,
                                  int aggregation, float* G, d3f_stream stream);
 int d3f_kpconv_grads_from_gathered(const float* G, const float* x, const float* weights, int n_supports, int K, int c_in,
-                                   int c_out, float* grad_x, float* grad_weights, d3f_stream stream);
+                                   int c_out, float* grad_x, float* grad_weights, int grad_weights_prezeroed,
+                                   d3f_stream stream);
 
 /* ------------------------------------------------------------------------------------------
  * Pairwise descriptor distance + descriptor loss + detector loss.  Replaces cdist,
@@ -239,10 +240,13 @@ int d3f_pair_loss_backward(const float* anchor, const float* positive, int P, in
  */
 /* out[n] = sum over rows of x[n_rows, n_cols] (bias gradients of the fused UnaryBlock) */
 int d3f_colsum(const float* x, int n_rows, int n_cols, float* out, d3f_stream stream);
+int d3f_colsum_prezeroed(const float* x, int n_rows, int n_cols, float* out, d3f_stream stream);
 /* LeakyReLU backward fused with the bias gradient: dz = grad * (y > 0 ? 1 : slope) with y the saved activation OUTPUT,
  * colsum[n] = sum_m dz[m, n].  n_cols must be 4 * 2^j with 16-byte aligned buffers, else D3F_ERR_UNSUPPORTED. */
 int d3f_leaky_backward_colsum(const float* grad, const float* y, float slope, int n_rows, int n_cols, float* dz,
                               float* colsum, d3f_stream stream);
+int d3f_leaky_backward_colsum_prezeroed(const float* grad, const float* y, float slope, int n_rows, int n_cols, float* dz,
+                                        float* colsum, d3f_stream stream);
 int d3f_max_pool_forward(const float* x, const void* inds, int idx_is_64, int64_t ld_inds, int n_queries,
                          int n_supports, int n_neighbors, int channels, const int32_t* valid_width, float* out,
                          int32_t* argmax, d3f_stream stream);
@@ -283,6 +287,9 @@ int d3f_mutual_nn(const float* source, const float* target, int n_source, int n_
 int d3f_gemm(int trans_a, int trans_b, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
              float* C, int ldc, const float* row_scale, const float* k_scale, const float* bias,
              int leaky_relu, float slope, d3f_stream stream);
+int d3f_gemm_prezeroed(int trans_a, int trans_b, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                       float* C, int ldc, const float* row_scale, const float* k_scale, const float* bias,
+                       int leaky_relu, float slope, d3f_stream stream);
 /* Deterministic variant (the forward pass): long-K problems are split along K by a rule that depends on K only, the
  * partial tiles go to `workspace` (d3f_gemm_workspace_bytes(M, N, K) bytes, 0 when no split is needed) and are summed
  * in split order before row scale / bias / activation, so a row of C is bit-identical run to run and independent
@@ -307,9 +314,13 @@ int d3f_gemm_status_snapshot(int32_t* out, d3f_stream stream);
  *   params, grads, momentum_buf: n fp32 elements each, 16-byte aligned;  lr: device float (ExponentialLR multiplies it
  *   between epochs, training_3DMatch.py:77-80);  nonfinite_flag: device int32, OR-ed with 1 when check_finite != 0 and
  *   some gradient element is inf / nan; when the flag is non-zero the update is skipped.  The caller clears the flag.
+ *   zero_grads != 0: `grads` is cleared in the same pass (the next step's optimizer.zero_grad()).
+ * The *_prezeroed variants of d3f_gemm / d3f_colsum / d3f_leaky_backward_colsum are for outputs inside such a cleared
+ * gradient buffer: they accumulate (split-K / row-block partial sums, with atomics) without a zero fill of their own.
  */
-int d3f_sgd_step(float* params, const float* grads, float* momentum_buf, size_t n, const float* lr,
-                 float momentum, float weight_decay, int32_t* nonfinite_flag, int check_finite, d3f_stream stream);
+int d3f_sgd_step(float* params, float* grads, float* momentum_buf, size_t n, const float* lr,
+                 float momentum, float weight_decay, int32_t* nonfinite_flag, int check_finite, int zero_grads,
+                 d3f_stream stream);
 
 #ifdef __cplusplus
 }
