@@ -92,6 +92,42 @@ __global__ void nt_fill_kernel(const void* __restrict__ inds, long long ld, int 
     if (j >= 0 && j < ns) src[atomicAdd(&cursor[j], 1)] = i;
 }
 
+// The fill above places entries with atomic cursors, so the order INSIDE a list varies run to run; the backward gather
+// sums rows in list order, i.e. grad_x would not be bit-reproducible.  One warp per list puts it into
+// ascending query order: an entry's rank is the number of smaller entries (ties, i.e. a row that lists a support twice,
+// broken by position) -- counted from a shared-memory copy (lists hold ~H entries; longer ones are ranked from global
+// memory into the same place after a copy-out through registers in chunks).
+constexpr int NT_SORT_CAP = 256;     // entries per warp in shared memory
+__global__ void __launch_bounds__(256)
+nt_sort_kernel(const int* __restrict__ off, int ns, int* __restrict__ src) {
+    __shared__ int buf[8][NT_SORT_CAP];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * 8 + warp;
+    if (j >= ns) return;
+    const int b = off[j], n = off[j + 1] - b;
+    if (n <= 1) return;
+    if (n <= NT_SORT_CAP) {
+        int* s = buf[warp];
+        for (int t = lane; t < n; t += 32) s[t] = src[b + t];
+        __syncwarp();
+        for (int t = lane; t < n; t += 32) {
+            const int v = s[t];
+            int r = 0;
+            for (int u = 0; u < n; ++u) r += (s[u] < v) | ((s[u] == v) & (u < t));   // (a row that lists a support twice)
+            src[b + r] = v;
+        }
+        return;
+    }
+    // long list (in-degree above 256: only wide deformable-radius matrices): odd-even transposition in place
+    for (int pass = 0; pass < n; ++pass) {
+        for (int t = 2 * lane + (pass & 1); t + 1 < n; t += 64) {
+            const int a = src[b + t], c = src[b + t + 1];
+            if (a > c) { src[b + t] = c; src[b + t + 1] = a; }
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace
 
 extern "C" size_t d3f_neighbors_transpose_workspace_bytes(int n_supports) {
@@ -119,6 +155,8 @@ extern "C" int d3f_neighbors_transpose(const void* inds, int idx_is_64, int64_t 
     D3F_CHECK_LAUNCH();
     if (idx_is_64) nt_fill_kernel<true><<<blocks, 256, 0, stream>>>(inds, (long long)ld_inds, nq, H, ns, cursor, t_src);
     else nt_fill_kernel<false><<<blocks, 256, 0, stream>>>(inds, (long long)ld_inds, nq, H, ns, cursor, t_src);
+    D3F_CHECK_LAUNCH();
+    nt_sort_kernel<<<d3f_ceil_div(ns, 8), 256, 0, stream>>>(t_offsets, ns, t_src);   // deterministic list order
     D3F_CHECK_LAUNCH();
     return D3F_OK;
 }

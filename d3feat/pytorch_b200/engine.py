@@ -141,6 +141,7 @@ def collate_static(pts0, pts1, feat0, feat1, corr, dist_keypts, config, limits, 
     srch_s = search_stream if search_stream is not None else main
     with torch.cuda.stream(srch_s):
         r_normal = config.first_subsampling_dl * config.conv_radius
+        deferred = []
         for l, (has_conv, deform_conv, has_pool, deform_pool) in enumerate(levels):
             cap = caps[l]
             pyr.wait(('points', l))                      # (no-op for level 0 and without a side stream)
@@ -155,8 +156,8 @@ def collate_static(pts0, pts1, feat0, feat1, corr, dist_keypts, config, limits, 
                 r = r_normal * config.deform_radius / config.conv_radius if deform_pool else r_normal
                 pool_i = search(pts[l + 1], pts[l], lens[l + 1], lens[l], r, limits[l], cap, transposes and not deform_pool)
                 pyr.mark(('pools', l), search_stream)
-                up_i = search(pts[l], pts[l + 1], lens[l], lens[l + 1], 2 * r, limits[l], caps[l + 1])
-                pyr.mark(('upsamples', l), search_stream)
+                up_i = None     # only the decoder reads the upsampling matrices: searched after every encoder matrix
+                deferred.append((l, 2 * r))
             else:
                 pool_i, up_i = empty_idx, empty_idx
             out['points'].append(pts[l])
@@ -165,6 +166,9 @@ def collate_static(pts0, pts1, feat0, feat1, corr, dist_keypts, config, limits, 
             out['upsamples'].append(up_i)
             out['stack_lengths'].append(lens[l])
             r_normal *= 2
+        for l, r_up in deferred:
+            out['upsamples'][l] = search(pts[l], pts[l + 1], lens[l], lens[l + 1], r_up, limits[l], caps[l + 1])
+            pyr.mark(('upsamples', l), search_stream)
     if search_stream is None and side_stream is not None:
         main.wait_stream(side_stream)    # searches ran on the main stream: everything the consumer needs is ordered
     out['features'] = feats

@@ -152,8 +152,8 @@ int d3f_kpconv_backward(const float* q_pts, const float* s_pts, const void* inds
                         void* workspace, size_t workspace_bytes, d3f_stream stream);
 
 /* Transposed neighbour lists for the atomic-free backward: for every support j the queries i with inds[i, h] = j
- * (any h), as CSR:  t_offsets [n_supports + 1] i32,  t_src [n_queries * n_neighbors capacity] i32 (query indices; the
- * order inside a list is unspecified).  One call per neighbour matrix; every KPConv layer that uses the matrix shares it.
+ * (any h), as CSR:  t_offsets [n_supports + 1] i32,  t_src [n_queries * n_neighbors capacity] i32 (query indices in
+ * ascending order inside a list, so the backward that sums in list order is bit-reproducible).  One call per neighbour matrix; every KPConv layer that uses the matrix shares it.
  * d3f_kpconv_backward_ex = d3f_kpconv_backward plus (t_offsets, t_src): when both are given and the layer is rigid with
  * Cout % 32 == 0, grad_x is computed as a forward-style gather over the lists followed by one GEMM with W^T -- no float
  * atomics (the 45 M reductions of level 0 cost 200 us however they are issued) and a deterministic result per list order;

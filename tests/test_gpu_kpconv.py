@@ -205,3 +205,20 @@ def test_fused_kernel_many_batches_vs_oracle(cuda, built_lib, nq, ns, H, idx_dty
         assert built_lib.d3f_gemm_tcgen05_failed() == 0
     finally:
         built_lib.d3f_set_kpconv_impl(-1)
+
+
+def test_transposed_lists_are_sorted_and_backward_is_reproducible(cuda):
+    """d3f_neighbors_transpose lists queries in ascending order (also lists above the 256-entry shared-memory path), so
+    the list-based grad_x is bit-identical run to run (atomic fill order)."""
+    from d3feat.pytorch_b200 import ops
+    rng = np.random.default_rng(5)
+    for nq, ns, H in ((3000, 700, 35), (900, 2, 2)):          # in-degrees ~150 and 900 (> 256: the in-place path)
+        inds = torch.from_numpy(np.stack([rng.permutation(ns + 1)[:H] for _ in range(nq)]).astype(np.int32)).to(cuda)
+        t_off, t_src = ops.neighbors_transpose(inds, ns)
+        off, src = t_off.cpu().numpy(), t_src.cpu().numpy()
+        for j in range(ns):
+            seg = src[off[j]:off[j + 1]]
+            assert np.all(np.diff(seg) > 0), j
+            assert np.array_equal(seg, np.nonzero((inds.cpu().numpy() == j).any(1))[0])
+        again = ops.neighbors_transpose(inds, ns)
+        assert torch.equal(again[0], t_off) and torch.equal(again[1][:off[-1]], t_src[:off[-1]])
