@@ -184,13 +184,17 @@ kp2_correlate_kernel(Kp2Args a, int HP, float* __restrict__ wf, float* __restric
     }
     const float* __restrict__ x = a.x;
     const int cin = a.cin;
+    // gridDim.y > 1: one 32*CG-channel chunk per blockIdx.y (deep levels: a few hundred queries x 256-512 channels would
+    // otherwise occupy 32-96 CTAs for tens of microseconds of pure latency)
+    const int c_lo = gridDim.y > 1 ? (int)blockIdx.y * 32 * CG : 0;
+    const int c_hi = gridDim.y > 1 ? min(cin, c_lo + 32 * CG) : cin;
 
     if (MODE == 0) {
         // ---- C (FFMA): lanes over channels, U rows in flight.  Row offsets are 32-bit (the launcher checks
         // Ns * Cin < 2^31); lanes beyond Cin read channel Cin-1 and drop the result, so the loop has no predicates.
         const int hr = (wp.hend + U - 1) & ~(U - 1);
         const unsigned ucin = (unsigned)cin;
-        for (int c0 = 0; c0 < cin; c0 += 32 * CG) {
+        for (int c0 = c_lo; c0 < c_hi; c0 += 32 * CG) {
             float acc[CG][KP];
             const float* xc[CG];
 #pragma unroll
@@ -248,7 +252,7 @@ kp2_correlate_kernel(Kp2Args a, int HP, float* __restrict__ wf, float* __restric
         // ---- C (tensor cores): wf[16 x 32*CG] = w[16 x 8] * X[8 x 32*CG] per 8 neighbours, 3xTF32
         const int gq = lane >> 2, tq = lane & 3;
         const int hr = (wp.hend + 7) & ~7;
-        for (int c0 = 0; c0 < cin; c0 += 32 * CG) {
+        for (int c0 = c_lo; c0 < c_hi; c0 += 32 * CG) {
             float acc[CG][4][4];
 #pragma unroll
             for (int j = 0; j < CG; ++j)
@@ -525,7 +529,9 @@ kp2t_correlate_kernel(Kp2tArgs a, float* __restrict__ G) {
     const int cout = a.cout;
     const float* __restrict__ g = a.g;
 
-    for (int c0 = 0; c0 < cout; c0 += 32 * CG) {
+    const int c_lo = gridDim.y > 1 ? (int)blockIdx.y * 32 * CG : 0;          // one channel chunk per blockIdx.y (small grids)
+    const int c_hi = gridDim.y > 1 ? min(cout, c_lo + 32 * CG) : cout;
+    for (int c0 = c_lo; c0 < c_hi; c0 += 32 * CG) {
         float acc[CG][4][4];
 #pragma unroll
         for (int jj = 0; jj < CG; ++jj)
@@ -646,12 +652,14 @@ template <bool IDX64, bool DEF, int MODE>
 int correlate_cg(const Kp2Args& a, int HP, int grid, int warps, size_t smem, float* wf, float* wf_unmod, float* inv_n,
                  float* min_d2, cudaStream_t stream) {
     const int cg = a.cin <= 32 ? 1 : (a.cin <= 64 ? 2 : 4);
+    const int chunks = (a.cin + 32 * cg - 1) / (32 * cg);
+    const dim3 grid2(grid, (chunks > 1 && grid < 2 * 148) ? chunks : 1);
 #define KP2_GO(CG_)                                                                                       \
     do {                                                                                                  \
         auto kern = kp2_correlate_kernel<IDX64, DEF, CG_, MODE>;                                          \
         int rc_ = kp2_set_smem(kern, smem);                                                               \
         if (rc_) return rc_;                                                                              \
-        kern<<<grid, warps * 32, smem, stream>>>(a, HP, wf, wf_unmod, inv_n, min_d2);                     \
+        kern<<<grid2, warps * 32, smem, stream>>>(a, HP, wf, wf_unmod, inv_n, min_d2);                    \
     } while (0)
     if (cg == 1) KP2_GO(1); else if (cg == 2) KP2_GO(2); else KP2_GO(4);
 #undef KP2_GO
@@ -754,12 +762,15 @@ int kp2t_correlate_launch(const Kp2tArgs& a, float* G, cudaStream_t stream) {
     const int warps = 8;
     const size_t smem = kp2t_warp_floats() * sizeof(float) * warps;
     const int grid = d3f_ceil_div(a.ns, warps);
+    const int cgt = a.cout <= 32 ? 1 : (a.cout <= 64 ? 2 : 4);
+    const int chunks = (a.cout + 32 * cgt - 1) / (32 * cgt);
+    const dim3 grid2(grid, (chunks > 1 && grid < 2 * 148) ? chunks : 1);
 #define KP2T_GO(CG_)                                                                                      \
     do {                                                                                                  \
         auto kern = kp2t_correlate_kernel<CG_>;                                                           \
         int rc_ = kp2_set_smem(kern, smem);                                                               \
         if (rc_) return rc_;                                                                              \
-        kern<<<grid, warps * 32, smem, stream>>>(a, G);                                                   \
+        kern<<<grid2, warps * 32, smem, stream>>>(a, G);                                                  \
     } while (0)
     if (a.cout <= 32) KP2T_GO(1); else if (a.cout <= 64) KP2T_GO(2); else KP2T_GO(4);
 #undef KP2T_GO
