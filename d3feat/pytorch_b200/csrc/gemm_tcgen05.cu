@@ -27,14 +27,20 @@ constexpr int A_TILE = (BK / 4) * A_LBO;              // 18560
 // the N tile is a template parameter (32 / 64 / 128): skinny outputs do not pay for a half-empty MMA and wide ones
 // re-read A half as often
 template <int BN> struct Cfg {
-    static constexpr int B_LBO = (BN / 8) * SBO + 16;
-    static constexpr int B_TILE = (BK / 4) * B_LBO;
-    static constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;   // hi + lo for A and B
+    // BN <= 64: the tf32-hi and remainder tiles of B are STACKED along N (rows 0..BN-1 = hi, BN..2BN-1 = lo of one
+    // K-major tile), so that one MMA of width 2*BN yields a_hi*b_hi and a_hi*b_lo side by side in the accumulator and a
+    // K step costs 2 tensor-core instructions instead of 3.  tools/umma_probe.cu measured >= 49 cycles per tcgen05.mma
+    // whatever N <= 96: with 3-4 co-resident CTAs the skinny GEMMs were bound by the NUMBER of MMAs, not by their math.
+    static constexpr bool STACK = BN <= 64;
+    static constexpr int B_LBO = ((STACK ? 2 * BN : BN) / 8) * SBO + 16;
+    static constexpr int B_TILE = (BK / 4) * B_LBO;               // STACK: holds hi and lo
+    static constexpr int B_LO_OFF = STACK ? (BN / 8) * SBO : B_TILE;   // byte offset of the remainder rows / tile
+    static constexpr int STAGE_BYTES = 2 * A_TILE + (STACK ? 1 : 2) * B_TILE;   // A hi + lo, B hi + lo
     // ONE shared-memory stage: these GEMMs are short (K = 32..960 for most of them) and latency-bound, so the
     // latency is hidden by co-resident CTAs (4 per SM at 46-56 KB) rather than by a deep pipeline inside one CTA
     // (ncu, round 1: 2 stages -> 1-2 CTAs/SM, 12-22 % warps active, every pipe under 27 %).
     static constexpr int SMEM_BYTES = STAGE_BYTES + 64;           // one stage + barrier / tmem pointer
-    static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    static constexpr uint32_t TMEM_COLS = STACK ? (2 * BN < 32 ? 32 : 2 * BN) : BN;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -102,7 +108,8 @@ __device__ unsigned long long g_tc5_t[32];
 template <bool TA, bool TB, int BN>
 __global__ void __launch_bounds__(NT, BN >= 128 ? 3 : 4)
 tc5_gemm_kernel(D3fGemm g) {
-    constexpr int B_LBO = Cfg<BN>::B_LBO, B_TILE = Cfg<BN>::B_TILE, STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
+    constexpr int B_LBO = Cfg<BN>::B_LBO, B_LO_OFF = Cfg<BN>::B_LO_OFF, STAGE_BYTES = Cfg<BN>::STAGE_BYTES;
+    constexpr bool STACK = Cfg<BN>::STACK;
     constexpr uint32_t TMEM_COLS = Cfg<BN>::TMEM_COLS;
     extern __shared__ __align__(128) char smem[];
     uint64_t* bars = (uint64_t*)(smem + STAGE_BYTES);          // [0]: the MMAs of the current K tile are done
@@ -131,6 +138,7 @@ tc5_gemm_kernel(D3fGemm g) {
     // b_major [16] | N>>3 [17,23) | M>>4 [24,29)
     // (both operands are fed K-major: a_major = b_major = 0)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
     float4 ra[4], rb[BN >= 128 ? BN / 32 : 4];
     auto load_tile = [&](int k0) {
@@ -168,7 +176,7 @@ tc5_gemm_kernel(D3fGemm g) {
         char* a_hi = smem;
         char* a_lo = a_hi + A_TILE;
         char* b_hi = a_lo + A_TILE;
-        char* b_lo = b_hi + B_TILE;
+        char* b_lo = b_hi + B_LO_OFF;
         if (!TA) {
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
@@ -226,16 +234,23 @@ tc5_gemm_kernel(D3fGemm g) {
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const uint32_t a_hi = smem_u32(smem), a_lo = a_hi + A_TILE;
-            const uint32_t b_hi = a_lo + A_TILE, b_lo = b_hi + B_TILE;
+            const uint32_t b_hi = a_lo + A_TILE, b_lo = b_hi + B_LO_OFF;
 #pragma unroll
             for (int ks = 0; ks < BK / 8; ++ks) {
                 // one MMA = 8 k values = two 16-byte k units
                 const uint32_t ao = ks * 2 * A_LBO, bo = ks * 2 * B_LBO;
                 const uint64_t dah = make_desc(a_hi + ao, A_LBO, SBO), dal = make_desc(a_lo + ao, A_LBO, SBO);
-                const uint64_t dbh = make_desc(b_hi + bo, B_LBO, SBO), dbl = make_desc(b_lo + bo, B_LBO, SBO);
-                mma_tf32(tmem_d, dal, dbh, idesc, (kt | ks) ? 1u : 0u);
-                mma_tf32(tmem_d, dah, dbl, idesc, 1u);
-                mma_tf32(tmem_d, dah, dbh, idesc, 1u);
+                const uint64_t dbh = make_desc(b_hi + bo, B_LBO, SBO);
+                if (STACK) {
+                    // D[:, 0:BN] += a_hi b_hi + a_lo b_hi,  D[:, BN:2BN] += a_hi b_lo   (added in the epilogue)
+                    mma_tf32(tmem_d, dah, dbh, idesc2, (kt | ks) ? 1u : 0u);   // B rows 0..2BN-1 = hi | lo
+                    mma_tf32(tmem_d, dal, dbh, idesc, 1u);
+                } else {
+                    const uint64_t dbl = make_desc(b_lo + bo, B_LBO, SBO);
+                    mma_tf32(tmem_d, dal, dbh, idesc, (kt | ks) ? 1u : 0u);
+                    mma_tf32(tmem_d, dah, dbl, idesc, 1u);
+                    mma_tf32(tmem_d, dah, dbh, idesc, 1u);
+                }
             }
             // tcgen05.commit: arrive on the barrier when every MMA issued so far has completed
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
@@ -264,7 +279,18 @@ tc5_gemm_kernel(D3fGemm g) {
                              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
                                "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                              : "r"(taddr) : "memory");
-                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+                if (STACK) {        // the a_hi * b_lo half of the accumulator sits BN columns further
+                    uint32_t u[16];
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                                   "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+                                 : "r"(taddr + (uint32_t)BN) : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(u[e]));
+                } else {
+                    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+                }
             } else {
 #pragma unroll
                 for (int e = 0; e < 16; ++e) v[e] = 0u;
