@@ -264,6 +264,11 @@ static int gemm_impl() {
     return g_gemm_impl;
 }
 
+// debug / tuning (include/d3feat_b200_debug.h): force the N tile width and the number of atomically combined K splits
+static int g_force_bn = 0, g_force_splits = 0;
+extern "C" void d3f_set_gemm_tuning(int bn, int splits) { g_force_bn = bn; g_force_splits = splits; }
+int d3f_gemm_forced_bn() { return g_force_bn; }
+
 int d3f_gemm_launch(const D3fGemm& in, bool ta, bool tb, cudaStream_t stream, float* det_ws, size_t det_ws_bytes) {
     D3fGemm g = in;
     g.partial = nullptr;
@@ -288,6 +293,7 @@ int d3f_gemm_launch(const D3fGemm& in, bool ta, bool tb, cudaStream_t stream, fl
             splits = min(d3f_ceil_div(592, tiles), d3f_ceil_div(g.K, 2 * BK));
             if (splits < 1) splits = 1;
         }
+        if (g_force_splits > 0 && plain && g.K > 0) splits = min(g_force_splits, d3f_ceil_div(g.K, BK));
         kps = d3f_ceil_div(d3f_ceil_div(g.K > 0 ? g.K : 1, splits), BK) * BK;
         splits = d3f_ceil_div(g.K > 0 ? g.K : 1, kps);
         const size_t c_floats = g.ctrans ? (size_t)(g.M / g.cblk) * g.cblk_stride

@@ -389,8 +389,14 @@ static int launch_bn(const D3fGemm& g, int splits, cudaStream_t stream) {
     return D3F_OK;
 }
 
+int d3f_gemm_forced_bn();
+
 template <bool TA, bool TB>
 static int launch_mode(const D3fGemm& g, int splits, cudaStream_t stream) {
+    const int forced = d3f_gemm_forced_bn();
+    if (forced == 32) return launch_bn<TA, TB, 32>(g, splits, stream);
+    if (forced == 64) return launch_bn<TA, TB, 64>(g, splits, stream);
+    if (forced == 128) return launch_bn<TA, TB, 128>(g, splits, stream);
     if (g.N <= 32) return launch_bn<TA, TB, 32>(g, splits, stream);
     // wide outputs with enough row tiles to fill the chip: 128-wide tiles halve the A re-reads
     if (g.N >= 256 && d3f_ceil_div(g.M, BM) * d3f_ceil_div(g.N, 128) * splits >= 148)

@@ -27,6 +27,9 @@ void d3f_kpconv_set_gather_events(void* start_event, void* stop_event);
 
 /* GEMM back end: 1 = tcgen05.mma + TMEM (default), 0 = legacy mma.sync. */
 void d3f_set_gemm_impl(int use_tcgen05);
+/* Tuning hook of tools/gemm_tune.py: force the N tile width (32 / 64 / 128, 0 = heuristic) of the tcgen05 GEMM and the
+ * number of atomically combined K splits of plain (epilogue-free) GEMMs (0 = heuristic). */
+void d3f_set_gemm_tuning(int bn, int splits);
 /* 1 if a tcgen05 kernel ever gave up waiting on its mbarrier (synchronises the device; the asynchronous form is
  * d3f_gemm_status_snapshot in d3feat_b200.h). */
 int d3f_gemm_tcgen05_failed(void);
