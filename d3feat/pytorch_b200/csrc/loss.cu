@@ -273,6 +273,71 @@ int pl_check(int P, int D, int loss_kind, int metric) {
     return D3F_OK;
 }
 
+// ---- detector loss on an ARBITRARY distance matrix (utils/loss.py:149-158), for callers that do not come through
+// CircleLoss / ContrastiveLoss of this package (any [P,P] fp32 matrix, e.g. a cdist):
+//   fp_i = max_j dists[i,j]·[i==j]  (= max(d_ii, 0) for P > 1),  cn_i = min_j dists[i,j] + 1e5·[i==j],
+//   loss = mean_i (fp_i - cn_i)·(anc_i + pos_i).
+// One warp per row; ties take the smallest column (torch leaves them unspecified); fixed-order final sum.
+__global__ void __launch_bounds__(256)
+det_rows_kernel(const float* __restrict__ dists, int ld, int P, float* __restrict__ rowval, int* __restrict__ arg) {
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= P) return;
+    const float* row = dists + (size_t)i * ld;
+    float best = INFINITY;
+    int bj = 0x7fffffff;
+    bool nan_seen = false;
+    for (int j = lane; j < P; j += 32) {
+        const float v = j == i ? __fadd_rn(row[j], 1e5f) : row[j];
+        nan_seen |= v != v;
+        if (v < best || (v == best && j < bj)) { best = v; bj = j; }
+    }
+    for (int o = 16; o; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+        if (ov < best || (ov == best && oj < bj)) { best = ov; bj = oj; }
+    }
+    nan_seen = __any_sync(0xffffffffu, nan_seen);
+    if (lane == 0) {
+        const float dii = row[i];
+        const bool diag = P == 1 || dii > 0.f;
+        const float fp = diag ? dii : (dii != dii ? dii : 0.f);
+        rowval[i] = nan_seen ? NAN : fp - best;
+        arg[i] = diag ? i : -1;
+        arg[P + i] = bj == 0x7fffffff ? -1 : bj;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+det_final_kernel(const float* __restrict__ rowval, const float* __restrict__ anc, const float* __restrict__ pos, int P,
+                 float* __restrict__ loss) {
+    __shared__ double sh[256];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < P; i += 256) acc += (double)(rowval[i] * (anc[i] + pos[i]));
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) loss[0] = (float)(sh[0] / (double)P);
+}
+
+__global__ void __launch_bounds__(256)
+det_grad_kernel(const float* __restrict__ rowval, const int* __restrict__ arg, const float* __restrict__ anc,
+                const float* __restrict__ pos, int P, const float* __restrict__ grad_loss, float* __restrict__ grad_dists,
+                int ld, float* __restrict__ grad_anc, float* __restrict__ grad_pos) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= P) return;
+    const float g = grad_loss[0] / (float)P;
+    if (grad_anc) grad_anc[i] = g * rowval[i];
+    if (grad_pos) grad_pos[i] = g * rowval[i];
+    if (grad_dists) {      // zero-filled by the caller of this kernel; one thread owns row i
+        const float gs = g * (anc[i] + pos[i]);
+        if (arg[i] >= 0) grad_dists[(size_t)i * ld + arg[i]] += gs;
+        if (arg[P + i] >= 0) grad_dists[(size_t)i * ld + arg[P + i]] -= gs;
+    }
+}
+
 }  // namespace
 
 extern "C" size_t d3f_pair_loss_aux_floats(int P) {
@@ -338,5 +403,34 @@ extern "C" int d3f_pair_loss_backward(const float* anchor, const float* positive
                                                                      grad_pos_score);
         D3F_CHECK_LAUNCH();
     }
+    return D3F_OK;
+}
+
+// Detector loss of utils/loss.py:149-158 on any [P,P] fp32 distance matrix (row stride ld).
+//   loss [1] out; rowval [P] (fp - cn per row) and arg [2P] (column of the furthest positive or -1, column of the closest
+//   negative) are kept for the backward.
+extern "C" int d3f_det_loss_forward(const float* dists, int ld, const float* anc_score, const float* pos_score, int P,
+                                    float* loss, float* rowval, int32_t* arg, d3f_stream stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    D3F_REQUIRE(P >= 1 && ld >= P, D3F_ERR_INVALID, "bad arguments");
+    D3F_REQUIRE(dists && anc_score && pos_score && loss && rowval && arg, D3F_ERR_INVALID, "null pointer");
+    det_rows_kernel<<<d3f_ceil_div(P, 8), 256, 0, stream>>>(dists, ld, P, rowval, arg);
+    D3F_CHECK_LAUNCH();
+    det_final_kernel<<<1, 256, 0, stream>>>(rowval, anc_score, pos_score, P, loss);
+    D3F_CHECK_LAUNCH();
+    return D3F_OK;
+}
+
+// grad_loss [1] (device).  grad_dists [P,P] (row stride ld; zero-filled here) or NULL; grad_anc_score / grad_pos_score [P] or NULL.
+extern "C" int d3f_det_loss_backward(const float* rowval, const int32_t* arg, const float* anc_score, const float* pos_score,
+                                     int P, const float* grad_loss, float* grad_dists, int ld, float* grad_anc_score,
+                                     float* grad_pos_score, d3f_stream stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    D3F_REQUIRE(P >= 1 && (!grad_dists || ld >= P), D3F_ERR_INVALID, "bad arguments");
+    D3F_REQUIRE(rowval && arg && anc_score && pos_score && grad_loss, D3F_ERR_INVALID, "null pointer");
+    if (grad_dists) D3F_CHECK_CUDA(cudaMemsetAsync(grad_dists, 0, sizeof(float) * (size_t)P * ld, stream));
+    det_grad_kernel<<<d3f_ceil_div(P, 256), 256, 0, stream>>>(rowval, arg, anc_score, pos_score, P, grad_loss, grad_dists, ld,
+                                                            grad_anc_score, grad_pos_score);
+    D3F_CHECK_LAUNCH();
     return D3F_OK;
 }

@@ -8,7 +8,7 @@ values (loss.py:111-141, 55-97, 149-158).  ``PairLoss`` is the fused form of the
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import _lib, ops
 
 
 def cdist(a, b, metric='euclidean'):
@@ -127,7 +127,56 @@ class ContrastiveLoss(nn.Module):
         return desc, acc, fp.tolist(), an.tolist(), 0, dists
 
 
+class _DetLossFunction(torch.autograd.Function):
+    """utils/loss.py:149-158 on an arbitrary distance matrix (d3f_det_loss_forward / _backward)."""
+
+    @staticmethod
+    def forward(ctx, dists, anc_score, pos_score):
+        lib = _lib.load()
+        if not dists.is_cuda:
+            raise RuntimeError("DetLoss: CUDA tensors only (there is no CPU path)")
+        d = dists.detach().float().contiguous()
+        P = d.shape[0]
+        if d.dim() != 2 or d.shape[1] != P or anc_score.numel() != P or pos_score.numel() != P:
+            raise RuntimeError("DetLoss: dists must be [P,P] and the scores [P] or [P,1]")
+        a = anc_score.detach().float().reshape(-1).contiguous()
+        b = pos_score.detach().float().reshape(-1).contiguous()
+        loss = torch.empty(1, dtype=torch.float32, device=d.device)
+        rowval = torch.empty(P, dtype=torch.float32, device=d.device)
+        arg = torch.empty(2 * P, dtype=torch.int32, device=d.device)
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.d3f_det_loss_forward(d.data_ptr(), P, a.data_ptr(), b.data_ptr(), P, loss.data_ptr(),
+                                            rowval.data_ptr(), arg.data_ptr(), st))
+        ctx.save_for_backward(rowval, arg, a, b)
+        ctx.shapes = (dists.shape, anc_score.shape, pos_score.shape, dists.dtype)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, grad):
+        lib = _lib.load()
+        rowval, arg, a, b = ctx.saved_tensors
+        P = rowval.shape[0]
+        dshape, ashape, bshape, ddtype = ctx.shapes
+        g = grad.detach().float().reshape(1).contiguous()
+        gd = torch.empty((P, P), dtype=torch.float32, device=g.device) if ctx.needs_input_grad[0] else None
+        ga = torch.empty(P, dtype=torch.float32, device=g.device) if ctx.needs_input_grad[1] else None
+        gb = torch.empty(P, dtype=torch.float32, device=g.device) if ctx.needs_input_grad[2] else None
+        _lib.check(lib.d3f_det_loss_backward(rowval.data_ptr(), arg.data_ptr(), a.data_ptr(), b.data_ptr(), P, g.data_ptr(),
+                                             None if gd is None else gd.data_ptr(), P,
+                                             None if ga is None else ga.data_ptr(), None if gb is None else gb.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream))
+        return (None if gd is None else gd.to(ddtype).reshape(dshape), None if ga is None else ga.reshape(ashape),
+                None if gb is None else gb.reshape(bshape))
+
+
 class DetLoss(nn.Module):
+    """DetLoss.forward(dists, anc_score, pos_score) of utils/loss.py:144-158.
+
+    `dists` returned by this package's CircleLoss / ContrastiveLoss carries the inputs it was computed from: the fused
+    pair-loss kernels then run again with the scores, so detector gradients reach the descriptors as they do through the
+    reference's un-detached `dists` (trainer.py:96-97).  Any OTHER [P,P] CUDA matrix (a clone, a slice, a cdist) takes
+    the stand-alone detector-loss kernels, differentiable in `dists` and both scores, as in the reference."""
+
     def __init__(self, metric='euclidean'):
         super().__init__()
         self.metric = metric
@@ -135,7 +184,7 @@ class DetLoss(nn.Module):
     def forward(self, dists, anc_score, pos_score):
         meta = getattr(dists, '_d3f_meta', None)
         if meta is None:
-            raise RuntimeError("DetLoss expects the `dists` returned by this package's CircleLoss/ContrastiveLoss")
+            return _DetLossFunction.apply(dists, anc_score, pos_score)
         _desc, det, *_ = _PairLossFunction.apply(
             meta['anchor'], meta['positive'], anc_score, pos_score, meta['dist_keypts'], meta['kind'],
             meta['metric'], meta['safe_radius'], meta['pos_margin'], meta['neg_margin'], meta['log_scale'])

@@ -222,6 +222,16 @@ int d3f_pair_loss_backward(const float* anchor, const float* positive, int P, in
                            float* grad_anchor, float* grad_positive,
                            float* grad_anc_score, float* grad_pos_score, d3f_stream stream);
 
+/* Detector loss of utils/loss.py:149-158 on ANY [P,P] fp32 distance matrix (row stride ld) -- the drop-in form of
+ * DetLoss.forward(dists, anc_score, pos_score) for matrices that do not come from d3f_pair_loss_forward.
+ * loss [1] out; rowval [P] f32 and arg [2P] i32 are kept for the backward.  grad_loss [1] (device); grad_dists [P,P]
+ * (zero-filled by the call) or NULL; grad_anc_score / grad_pos_score [P] or NULL. */
+int d3f_det_loss_forward(const float* dists, int ld, const float* anc_score, const float* pos_score, int P,
+                         float* loss, float* rowval, int32_t* arg, d3f_stream stream);
+int d3f_det_loss_backward(const float* rowval, const int32_t* arg, const float* anc_score, const float* pos_score,
+                          int P, const float* grad_loss, float* grad_dists, int ld, float* grad_anc_score,
+                          float* grad_pos_score, d3f_stream stream);
+
 /* ------------------------------------------------------------------------------------------
  * Gathers between the KPConv layers (they dominate a GPU training step
  * when left to ATen advanced indexing).  Shadow index (>= n_supports) reads a zero row.

@@ -77,3 +77,29 @@ def test_loss_gradients_other_metrics_vs_oracle(cuda, metric, kind):
     errs = dict(l=rel_err(o["desc_loss"].detach().cpu(), l.detach()), det=rel_err(o["det_loss"].detach().cpu(), det.detach()),
                 dA=rel_err(Ag.grad.cpu(), A.grad), dB=rel_err(Bg.grad.cpu(), B.grad), dS=rel_err(SAg.grad.cpu(), SA.grad))
     assert max(errs.values()) < TOL, errs
+
+
+@pytest.mark.parametrize("P", [1, 7, 300])
+def test_det_loss_on_an_arbitrary_distance_matrix_vs_oracle(cuda, P):
+    """DetLoss must accept ANY [P,P] matrix, as the reference does (utils/loss.py:149-158): a clone / cdist output has
+    lost the tag of this package's CircleLoss and takes the stand-alone kernels; value and all three gradients are compared
+    with the oracle's detector loss.  One diagonal entry is negative (furthest positive = 0, no gradient to it)."""
+    from oracle import model_ref
+    from d3feat.pytorch_b200.loss import DetLoss
+    rng = np.random.default_rng(P)
+    d = (rng.random((P, P)) * 2).astype(np.float32)
+    if P > 1:
+        d[P // 2, P // 2] = -0.3
+    sa, sp = rng.random((P, 1)).astype(np.float32), rng.random((P, 1)).astype(np.float32)
+    D = torch.from_numpy(d).requires_grad_(True); SA = torch.from_numpy(sa).requires_grad_(True); SP = torch.from_numpy(sp).requires_grad_(True)
+    ref = model_ref.det_loss(D, SA, SP)
+    (3.0 * ref).backward()
+    Dg = torch.from_numpy(d).to(cuda).requires_grad_(True)
+    SAg = torch.from_numpy(sa).to(cuda).requires_grad_(True); SPg = torch.from_numpy(sp).to(cuda).requires_grad_(True)
+    out = DetLoss()(Dg.clone(), SAg, SPg)
+    (3.0 * out).backward()
+    assert rel_err(out.detach().cpu(), ref.detach()) < TOL
+    assert rel_err(SAg.grad.cpu(), SA.grad) < TOL and rel_err(SPg.grad.cpu(), SP.grad) < TOL
+    assert rel_err(Dg.grad.cpu(), D.grad) < TOL
+    with pytest.raises(RuntimeError):
+        DetLoss()(torch.from_numpy(d), SA, SP)          # CPU tensors: no CPU path

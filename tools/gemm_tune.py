@@ -1,7 +1,8 @@
 """Sweep tile width / K splits of the tcgen05 GEMM over every GEMM shape of the pair step:
        python tools/gemm_tune.py [n_points]
 Logs the (M, N, K, transA, transB, mode) of every ops.gemm call of one eager training step, then times each unique plain
-shape warm (operands L2-resident, as inside the step where the producer has just written them) under the heuristic and
+shape warm (operands L2-resident, as inside the step where the producer has just written them; a spin kernel queued in
+front of each call hides the host's launch latency from the events) under the heuristic and
 under forced (BN, splits).  Output: one line per shape with the heuristic time, the best forced setting and its time."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -53,6 +54,7 @@ def time_one(M, N, K, ta, tb, mode, epi, reps=30):
     ts = []
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(300000)      # keep the GPU busy while the host enqueues: the events then bracket GPU time only
         e0.record(); ops.gemm(a, b, **kw); e1.record(); e1.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e3)
     return float(np.median(ts))
