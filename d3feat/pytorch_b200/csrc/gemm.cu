@@ -289,8 +289,14 @@ int d3f_gemm_launch(const D3fGemm& in, bool ta, bool tb, cudaStream_t stream, fl
             g.partial = det_ws;
         }
     } else {
-        if (g.K > 0 && plain && tiles < 296) {   // atomically combined partials: >= 2 K tiles per split, ~4 CTAs per SM
-            splits = min(d3f_ceil_div(592, tiles), d3f_ceil_div(g.K, 2 * BK));
+        if (g.K > 0 && plain) {
+            // atomically combined partials.  Fitted to the sweep of tools/gemm_tune.py over every GEMM of the step
+            // (profiles/r2_gemm_tune.txt): about two CTAs per SM in flight (more splits only add atomics and a zero
+            // fill: [13312 x 128 x 256] ran 36 us split in three, 25 us unsplit), never more than 16 K tiles in one
+            // CTA's serial loop ([256 x 768 x 13312]: 77 us at 12 splits, 60 us at 24), at least 2 K tiles per split.
+            const int kt = d3f_ceil_div(g.K, BK);
+            splits = max(296 / tiles, d3f_ceil_div(kt, 16));
+            splits = min(splits, kt / 2);
             if (splits < 1) splits = 1;
         }
         if (g_force_splits > 0 && plain && g.K > 0) splits = min(g_force_splits, d3f_ceil_div(g.K, BK));

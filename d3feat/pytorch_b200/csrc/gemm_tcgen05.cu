@@ -398,8 +398,9 @@ static int launch_mode(const D3fGemm& g, int splits, cudaStream_t stream) {
     if (forced == 64) return launch_bn<TA, TB, 64>(g, splits, stream);
     if (forced == 128) return launch_bn<TA, TB, 128>(g, splits, stream);
     if (g.N <= 32) return launch_bn<TA, TB, 32>(g, splits, stream);
-    // wide outputs with enough row tiles to fill the chip: 128-wide tiles halve the A re-reads
-    if (g.N >= 256 && d3f_ceil_div(g.M, BM) * d3f_ceil_div(g.N, 128) * splits >= 148)
+    // 128-wide tiles halve the A re-reads but cost 3 MMAs per K step where the stacked 64-wide tile costs 2: they win
+    // only on the largest problems (profiles/r2_gemm_tune.txt: >= 2.2 GFLOP won by 5-12 %, <= 0.54 GFLOP lost by 10-30 %)
+    if (g.N >= 256 && (double)g.M * g.N * g.K >= 1.0e9 && d3f_ceil_div(g.M, BM) * d3f_ceil_div(g.N, 128) * splits >= 148)
         return launch_bn<TA, TB, 128>(g, splits, stream);
     return launch_bn<TA, TB, 64>(g, splits, stream);
 }
