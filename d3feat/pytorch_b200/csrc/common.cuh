@@ -47,6 +47,20 @@ struct WsCursor {
 };
 
 __host__ __device__ static inline int d3f_ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// fill.cu: up to 6 regions of 32-bit words, each set to its own pattern, in ONE kernel launch
+struct D3fFillSegs {
+    void* p[6];
+    size_t words[6];
+    uint32_t v[6];
+    int n;
+    D3fFillSegs() : n(0) {}
+    void add(void* ptr, size_t bytes, uint32_t pattern) {
+        if (bytes == 0) return;
+        p[n] = ptr; words[n] = bytes / 4; v[n] = pattern; ++n;
+    }
+};
+int d3f_fill_segments(const D3fFillSegs& s, cudaStream_t stream);
 __host__ __device__ static inline uint32_t d3f_pow2ceil(uint32_t v) {
     uint32_t p = 1; while (p < v) p <<= 1; return p;
 }

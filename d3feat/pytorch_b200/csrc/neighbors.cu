@@ -243,8 +243,10 @@ extern "C" int d3f_radius_neighbors(const float* queries, const float* supports,
     D3F_REQUIRE(out_idx == nullptr || max_cols > 0, D3F_ERR_INVALID, "max_cols must be positive when out_idx is given");
     D3F_REQUIRE(row_capacity >= 64 && row_capacity <= 8192 && (row_capacity & (row_capacity - 1)) == 0,
                 D3F_ERR_INVALID, "row_capacity must be a power of two in [64, 8192]");
-    D3F_CHECK_CUDA(cudaMemsetAsync(out_info, 0, 4 * sizeof(int32_t), stream));
-    if (n_queries == 0) return D3F_OK;
+    if (n_queries == 0) {
+        D3F_CHECK_CUDA(cudaMemsetAsync(out_info, 0, 4 * sizeof(int32_t), stream));
+        return D3F_OK;
+    }
     D3F_REQUIRE(queries && supports && q_lengths && s_lengths, D3F_ERR_INVALID, "null input");
     NbWs w;
     size_t need = nb_layout(&w, workspace, workspace_bytes, n_supports);
@@ -253,9 +255,14 @@ extern "C" int d3f_radius_neighbors(const float* queries, const float* supports,
     const float cs = radius * 1.01f;
     const float inv_cs = 1.0f / cs;
     const float r2 = radius * radius;  // neighbors.cpp:226 (fp32 product)
-    // keys..cursor are contiguous: one memset for cnt+cursor, one for keys
-    D3F_CHECK_CUDA(cudaMemsetAsync(w.keys, 0xFF, (size_t)w.table * sizeof(unsigned long long), stream));
-    D3F_CHECK_CUDA(cudaMemsetAsync(w.cnt, 0, (char*)w.start - (char*)w.cnt, stream));
+    {   // info vector, hash keys (empty = all ones) and the contiguous cnt + cursor block: one launch (fill.cu)
+        D3fFillSegs f;
+        f.add(out_info, 4 * sizeof(int32_t), 0u);
+        f.add(w.keys, (size_t)w.table * sizeof(unsigned long long), 0xFFFFFFFFu);
+        f.add(w.cnt, (size_t)((char*)w.start - (char*)w.cnt), 0u);
+        int rcf = d3f_fill_segments(f, stream);
+        if (rcf) return rcf;
+    }
     if (n_supports > 0) {
         const int T = 256;
         nb_insert_kernel<<<d3f_ceil_div(n_supports, T), T, 0, stream>>>(

@@ -360,19 +360,24 @@ extern "C" int d3f_grid_subsample(const float* points, const int32_t* lengths, i
     D3F_REQUIRE(lengths && out_lengths, D3F_ERR_INVALID, "null lengths");
     D3F_REQUIRE(sample_dl > 0.f, D3F_ERR_INVALID, "sample_dl must be positive");
     D3F_REQUIRE(n_points < (1 << 30), D3F_ERR_UNSUPPORTED, "too many points");
-    D3F_CHECK_CUDA(cudaMemsetAsync(out_lengths, 0, (n_batch + 1) * sizeof(int32_t), stream));
     D3F_REQUIRE(out_capacity >= 0, D3F_ERR_INVALID, "bad out_capacity");
-    if (out_points && out_capacity > 0) D3F_CHECK_CUDA(cudaMemsetAsync(out_points, 0, sizeof(float) * 3 * (size_t)out_capacity, stream));
-    if (n_points == 0) return D3F_OK;
+    D3fFillSegs f;          // every region this call initialises, cleared by ONE launch (fill.cu)
+    f.add(out_lengths, (size_t)(n_batch + 1) * sizeof(int32_t), 0u);
+    if (out_points && out_capacity > 0) f.add(out_points, sizeof(float) * 3 * (size_t)out_capacity, 0u);
+    if (n_points == 0) return d3f_fill_segments(f, stream);
     D3F_REQUIRE(points && out_points, D3F_ERR_INVALID, "null points");
     SubWs w;
     const size_t need = sub_layout(&w, workspace, workspace_bytes, n_points, n_batch);
     D3F_REQUIRE(workspace != nullptr && need <= workspace_bytes, D3F_ERR_WORKSPACE, "workspace too small");
 
     const int T = 256;
-    D3F_CHECK_CUDA(cudaMemsetAsync(w.keys, 0xFF, (size_t)w.table * 8, stream));
-    D3F_CHECK_CUDA(cudaMemsetAsync(w.cnt, 0, (char*)w.start - (char*)w.cnt, stream));  // cnt, cursor, info
-    D3F_CHECK_CUDA(cudaMemsetAsync(w.minidx, 0xFF, (size_t)w.table * 4, stream));
+    f.add(w.keys, (size_t)w.table * 8, 0xFFFFFFFFu);
+    f.add(w.cnt, (size_t)((char*)w.start - (char*)w.cnt), 0u);  // cnt, cursor, info
+    f.add(w.minidx, (size_t)w.table * 4, 0xFFFFFFFFu);
+    {
+        int rcf = d3f_fill_segments(f, stream);
+        if (rcf) return rcf;
+    }
     sub_bounds_kernel<<<n_batch, 1024, 0, stream>>>(points, lengths, n_batch, sample_dl, w.grid);
     D3F_CHECK_LAUNCH();
     sub_insert_kernel<<<d3f_ceil_div(n_points, T), T, 0, stream>>>(points, lengths, n_batch, n_points, sample_dl,

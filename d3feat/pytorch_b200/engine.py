@@ -209,6 +209,7 @@ class PairStep:
                        torch.zeros((num_node, num_node), dtype=torch.float64, device=dev))
         self.lengths0 = torch.tensor([n0, n1], dtype=torch.int32, device=dev)
         self.graph = None
+        self.zero_arena = None
         self.loss = torch.zeros((), **f32)
         self.desc_loss = torch.zeros((), **f32)
         self.det_loss = torch.zeros((), **f32)
@@ -227,8 +228,16 @@ class PairStep:
     # -- the step on the static input buffers
     def _body(self):
         # without an optimizer the step is forward + loss only: no autograd graph is recorded
-        with torch.set_grad_enabled(self.optimizer is not None):
-            return self._body_impl()
+        from . import ops
+        if self.zero_arena is None:
+            self.zero_arena = ops.ZeroArena()
+        prev, ops.ZERO_ARENA = ops.ZERO_ARENA, self.zero_arena
+        try:
+            with torch.set_grad_enabled(self.optimizer is not None):
+                self.zero_arena.reset()       # one fill for every split-K GEMM output of the step
+                return self._body_impl()
+        finally:
+            ops.ZERO_ARENA = prev
 
     def _body_impl(self):
         cfg = self.config

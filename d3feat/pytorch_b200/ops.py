@@ -518,6 +518,40 @@ def _prezeroed(t):
     return t is not None and getattr(t, "_d3f_prezeroed", False)
 
 
+class ZeroArena:
+    """Outputs of the atomically combined (split-K) GEMMs of one step, carved from ONE buffer that is cleared by ONE fill
+    at the top of the step instead of one memset node in front of every GEMM (58 of the 126 memset nodes of a captured pair
+    step, each on the critical path of a latency-bound chain).  engine.PairStep installs it as ops.ZERO_ARENA around its
+    body and calls reset() first; a view is handed out once per step and never reused inside it.  The buffer is sized by
+    the previous step (capture() warms up eagerly first); a request that does not fit falls back to torch.zeros."""
+
+    def __init__(self):
+        self.buf = None
+        self.off = 0          # floats handed out in this step
+        self.spilled = 0      # floats that did not fit in this step
+        self.high = 0         # floats handed out in the previous step (= what reset() has to clear)
+
+    def reset(self):
+        need = self.off + self.spilled
+        if self.buf is None or self.buf.numel() < need:
+            self.buf = torch.zeros(need, dtype=torch.float32, device="cuda") if need else None
+        elif self.off:
+            self.buf[:self.off].zero_()
+        self.high, self.off, self.spilled = self.off, 0, 0
+
+    def take(self, n, device):
+        n_al = (n + 31) & ~31                      # 128-byte granules: vector stores stay aligned
+        if self.buf is None or self.buf.device != device or self.off + n_al > self.buf.numel():
+            self.spilled += n_al
+            return torch.zeros(n, dtype=torch.float32, device=device)
+        v = self.buf[self.off:self.off + n]
+        self.off += n_al
+        return v
+
+
+ZERO_ARENA = None
+
+
 def gemm(a, b, trans_a=False, trans_b=False, row_scale=None, k_scale=None, bias=None, slope=None, deterministic=False,
          bias2=None, residual=None, out=None):
     """C = act(row_scale * opA(a) @ (k_scale * opB(b)) + bias + bias2 + residual) via d3f_gemm / d3f_gemm_ex
@@ -535,6 +569,11 @@ def gemm(a, b, trans_a=False, trans_b=False, row_scale=None, k_scale=None, bias=
         if out.numel() != M * N or out.dtype != torch.float32 or not out.is_contiguous():
             raise RuntimeError("gemm: `out` must be a contiguous fp32 tensor of %d elements" % (M * N))
         c = out
+    elif (ZERO_ARENA is not None and not deterministic and bias is None and slope is None and bias2 is None
+          and residual is None):
+        # a plain GEMM may split K and combine its partials atomically: its output comes from the step's cleared arena
+        c = out = ZERO_ARENA.take(M * N, a.device).view(M, N)
+        c._d3f_prezeroed = True
     else:
         c = torch.empty((M, N), dtype=torch.float32, device=a.device)
     global launch_count
