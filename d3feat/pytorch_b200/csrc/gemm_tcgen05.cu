@@ -213,7 +213,7 @@ tc5_gemm_kernel(D3fGemm g) {
 
 #ifdef D3F_TC5_TIMING
     const bool timed = (tid == 0 || tid == 255) && blockIdx.x == 0 && blockIdx.y == gridDim.y / 2 && blockIdx.z == 0;
-    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+    long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
     const long long tstart = tlast;
 #endif
     bool ok = true;
@@ -300,55 +300,89 @@ tc5_gemm_kernel(D3fGemm g) {
                 *(uint4*)&cs[r_loc * LDC_S + col0 + part * 16 + e] = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
         }
     }
+    TC5_T(10);                                                                     // TMEM -> registers -> shared C tile
     __syncthreads();
+    TC5_T(11);
     {
+        // Shared C tile -> global.  This code runs ONCE per CTA: ncu's source page showed the former fully unrolled,
+        // every-mode-inlined version of it (2000 instructions) spending 47 % of a small GEMM's samples in
+        // stall_no_inst -- instruction-cache misses on straight-line code (3.5 us of a 7.4 us CTA).  Hence: a rolled loop,
+        // the column-invariant work (bias loads, bounds, address parts) hoisted, one compact body per store mode.
         const bool atomic = gridDim.z > 1 && !g.partial;
         constexpr int TPR = BN / 4, RPP = NT / TPR;      // threads per row, rows per pass
         const int c4 = (tid % TPR) * 4, n = n0 + c4;
+        const int nv = min(4, g.N - n);                  // valid columns of this thread's quad (<= 0: none)
         const bool vec_ok = g.partial ? ((g.N & 3) == 0) : ((g.ldc & 3) == 0 && (((size_t)g.C) & 15) == 0);
-#pragma unroll
-        for (int it = 0; it < BM / RPP; ++it) {
-            const int r_loc = tid / TPR + RPP * it, row = m0 + r_loc;
-            if (row >= g.M || n >= g.N) continue;
-            float4 x = *(const float4*)&cs[r_loc * LDC_S + c4];
-            if (!ok) x = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000), __int_as_float(0x7fc00000),
-                                     __int_as_float(0x7fc00000));
-            float xs[4] = {x.x, x.y, x.z, x.w};
+        const float qnan = __int_as_float(0x7fc00000);
+        if (nv > 0) {
             if (g.partial) {
-                float* dst = g.partial + (size_t)blockIdx.z * g.M * g.N + (size_t)row * g.N + n;
-                if (vec_ok && n + 3 < g.N) *(float4*)dst = x;
-                else for (int e = 0; e < 4; ++e) if (n + e < g.N) dst[e] = xs[e];
-                continue;
-            }
-            const float sc = g.rs ? g.rs[row] : 1.0f;
-            if (g.ctrans) {      // transposed column blocks (see gemm.cuh): scalar, element stride ldc
-                float* dt = g.C + (size_t)(row / g.cblk) * g.cblk_stride + (size_t)n * g.ldc + (row % g.cblk);
-                for (int e = 0; e < 4; ++e)
-                    if (n + e < g.N) {
-                        if (atomic) atomicAdd(dt + (size_t)e * g.ldc, xs[e] * sc);
-                        else dt[(size_t)e * g.ldc] = xs[e] * sc;
-                    }
-                continue;
-            }
-            float* dst = g.cblk ? g.C + (size_t)(n / g.cblk) * g.cblk_stride + (size_t)row * g.ldc + (n % g.cblk)
-                                : g.C + (size_t)row * g.ldc + n;
-            if (atomic) {
-                for (int e = 0; e < 4; ++e) if (n + e < g.N) atomicAdd(dst + e, xs[e] * sc);
-                continue;
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float y = xs[e] * sc;
-                if (n + e < g.N) {
-                    if (g.bias) y += g.bias[n + e];
-                    if (g.bias2) y += g.bias2[n + e];
-                    if (g.res) y += g.res[(size_t)row * g.ldr + n + e];
+                float* base = g.partial + (size_t)blockIdx.z * g.M * g.N + n;
+#pragma unroll 1
+                for (int r_loc = tid / TPR; r_loc < BM && m0 + r_loc < g.M; r_loc += RPP) {
+                    float4 x = *(const float4*)&cs[r_loc * LDC_S + c4];
+                    if (!ok) x = make_float4(qnan, qnan, qnan, qnan);
+                    float* dst = base + (size_t)(m0 + r_loc) * g.N;
+                    if (vec_ok && nv == 4) *(float4*)dst = x;
+                    else { const float xs[4] = {x.x, x.y, x.z, x.w}; for (int e = 0; e < nv; ++e) dst[e] = xs[e]; }
                 }
-                if (g.act) y = y > 0.f ? y : y * g.slope;
-                xs[e] = y;
+            } else if (g.ctrans) {     // transposed column blocks (see gemm.cuh): scalar, element stride ldc
+#pragma unroll 1
+                for (int r_loc = tid / TPR; r_loc < BM && m0 + r_loc < g.M; r_loc += RPP) {
+                    const int row = m0 + r_loc;
+                    float4 x = *(const float4*)&cs[r_loc * LDC_S + c4];
+                    if (!ok) x = make_float4(qnan, qnan, qnan, qnan);
+                    const float sc = g.rs ? g.rs[row] : 1.0f;
+                    const float xs[4] = {x.x * sc, x.y * sc, x.z * sc, x.w * sc};
+                    float* dt = g.C + (size_t)(row / g.cblk) * g.cblk_stride + (size_t)n * g.ldc + (row % g.cblk);
+                    for (int e = 0; e < nv; ++e) {
+                        if (atomic) atomicAdd(dt + (size_t)e * g.ldc, xs[e]);
+                        else dt[(size_t)e * g.ldc] = xs[e];
+                    }
+                }
+            } else {
+                float* cbase = g.cblk ? g.C + (size_t)(n / g.cblk) * g.cblk_stride + (n % g.cblk) : g.C + n;
+                float b1[4] = {0.f, 0.f, 0.f, 0.f}, b2[4] = {0.f, 0.f, 0.f, 0.f};
+                if (!atomic) {
+                    for (int e = 0; e < nv; ++e) {
+                        if (g.bias) b1[e] = g.bias[n + e];
+                        if (g.bias2) b2[e] = g.bias2[n + e];
+                    }
+                }
+#pragma unroll 1
+                for (int r_loc = tid / TPR; r_loc < BM && m0 + r_loc < g.M; r_loc += RPP) {
+                    const int row = m0 + r_loc;
+                    float4 x = *(const float4*)&cs[r_loc * LDC_S + c4];
+                    if (!ok) x = make_float4(qnan, qnan, qnan, qnan);
+                    const float sc = g.rs ? g.rs[row] : 1.0f;
+                    float xs[4] = {x.x * sc, x.y * sc, x.z * sc, x.w * sc};
+                    float* dst = cbase + (size_t)row * g.ldc;
+                    if (atomic) {
+                        for (int e = 0; e < nv; ++e) atomicAdd(dst + e, xs[e]);
+                        continue;
+                    }
+                    float rr[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (g.res) {
+                        const float* rp = g.res + (size_t)row * g.ldr + n;
+                        if (nv == 4 && (g.ldr & 3) == 0 && (((size_t)g.res) & 15) == 0) {
+                            const float4 t = *(const float4*)rp;
+                            rr[0] = t.x; rr[1] = t.y; rr[2] = t.z; rr[3] = t.w;
+                        } else {
+                            for (int e = 0; e < nv; ++e) rr[e] = rp[e];
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float y = xs[e];
+                        if (g.bias) y += b1[e];
+                        if (g.bias2) y += b2[e];
+                        if (g.res) y += rr[e];
+                        if (g.act) y = y > 0.f ? y : y * g.slope;
+                        xs[e] = y;
+                    }
+                    if (vec_ok && nv == 4) *(float4*)dst = make_float4(xs[0], xs[1], xs[2], xs[3]);
+                    else for (int e = 0; e < nv; ++e) dst[e] = xs[e];
+                }
             }
-            if (vec_ok && n + 3 < g.N) *(float4*)dst = make_float4(xs[0], xs[1], xs[2], xs[3]);
-            else for (int e = 0; e < 4; ++e) if (n + e < g.N) dst[e] = xs[e];
         }
     }
     TC5_T(7);                                                                      // epilogue
@@ -358,6 +392,8 @@ tc5_gemm_kernel(D3fGemm g) {
         for (int i = 0; i < 8; ++i) o[i] = (unsigned long long)tacc[i];
         o[8] = (unsigned long long)(clock64() - tstart);
         o[9] = (unsigned long long)nk;
+        o[10] = (unsigned long long)tacc[10];
+        o[11] = (unsigned long long)tacc[11];
     }
 #endif
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");

@@ -23,15 +23,22 @@ lib.d3f_tc5_timing.argtypes = [ctypes.c_void_p]
 from d3feat.pytorch_b200 import ops
 dev = torch.device("cuda:0")
 names = ["wait MMAs of previous tile (mbarrier)", "store_tile (incl. waiting for the global loads)", "issue next global loads",
-         "fence.proxy.async + tcgen05 fence", "__syncthreads", "MMA issue + commit (thread 0)", "prologue", "epilogue"]
+         "fence.proxy.async + tcgen05 fence", "__syncthreads", "MMA issue + commit (thread 0)", "prologue", "epilogue: shared C tile -> global", "", "",
+         "epilogue: TMEM -> registers -> shared C tile", "epilogue: __syncthreads"]
 shapes = [(40000, 32, 480, False, False, "L0 contraction"), (13312, 64, 960, False, False, "L1 contraction"),
-          (40000, 128, 32, False, True, "unary 32->128"), (480, 32, 40000, True, False, "L0 dW"), (768, 1024, 3072, False, True, "decoder unary")]
+          (40000, 128, 32, False, True, "unary 32->128"), (480, 32, 40000, True, False, "L0 dW"), (768, 1024, 3072, False, True, "decoder unary"),
+          (768, 1024, 256, False, False, "small dx"), (2816, 512, 128, False, True, "small unary"), (256, 1024, 768, True, False, "small dW"),
+          (13312, 128, 64, False, False, "tiny dx")]
 for (M, N, K, ta, tb, label) in shapes:
     a = torch.randn((K, M) if ta else (M, K), device=dev)
     b = torch.randn((N, K) if tb else (K, N), device=dev)
     for _ in range(3):
         ops.gemm(a, b, ta, tb, deterministic=not ta)
     torch.cuda.synchronize()
+    torch.cuda._sleep(300000)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); ops.gemm(a, b, ta, tb, deterministic=not ta); e1.record(); torch.cuda.synchronize()
+    print("%s: whole op %.1f us" % (label, e0.elapsed_time(e1) * 1e3))
     buf = (ctypes.c_ulonglong * 32)()
     assert lib.d3f_tc5_timing(buf) == 0
     for who, off in (("thread 0 (MMA issuer)", 0), ("thread 255", 16)):
@@ -39,4 +46,5 @@ for (M, N, K, ta, tb, label) in shapes:
         print("%s  M=%d N=%d K=%d ta=%d tb=%d | %s: CTA total %d cycles, %d K tiles, %.0f cycles per tile in the loop"
               % (label, M, N, K, ta, tb, who, tot, nk, sum(buf[off + i] for i in range(6)) / max(nk, 1)))
         for i, nme in enumerate(names):
+            if not nme: continue
             print("    %-52s %9d cycles  %5.1f %%" % (nme, buf[off + i], 100.0 * buf[off + i] / max(tot, 1)))
