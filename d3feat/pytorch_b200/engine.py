@@ -82,14 +82,15 @@ class _Pyramid:
 
 
 def collate_static(pts0, pts1, feat0, feat1, corr, dist_keypts, config, limits, caps, lengths=None, side_stream=None,
-                   transposes=False, search_stream=None):
+                   transposes=False, search_stream=None, transpose_stream=None):
     """Same pyramid as dataloader.collate_fn_descriptor (reference dataloader.py:69-189) on capacity-padded tensors,
     with no host synchronisation.  Returns (batch dict, pyramid); `pyramid.join()` gives the status int32 tensor, which
     must be all zeros for the batch to be valid (checked by the caller after the step).
 
     Streams.  The grid-subsampling chain (level l+1 needs level l only; its order kernel is one CTA per cloud, ~130 us
-    per level with 146 SMs idle) runs on `side_stream`, the radius searches (+ transposed lists) on `search_stream`,
-    and the CONSUMER -- the network on the current stream -- waits per tensor (batch['_pyramid'].wait(('neighbors', l))
+    per level with 146 SMs idle) runs on `side_stream`, the radius searches on `search_stream`, the transposed lists
+    (read by the backward pass only: with them on the search stream the first convolution started 140 us late) on
+    `transpose_stream`, each behind the event of its search, and the CONSUMER -- the network on the current stream -- waits per tensor (batch['_pyramid'].wait(('neighbors', l))
     in blocks._conv_geometry etc.), so the level-0 convolutions start as soon as the level-0 search is done while the
     deeper levels are still being built.  Inside a CUDA-graph capture this becomes a fork/join in the graph.  With both
     streams None everything runs in order on the current stream."""
@@ -103,7 +104,7 @@ def collate_static(pts0, pts1, feat0, feat1, corr, dist_keypts, config, limits, 
     empty_idx = torch.zeros((0, 1), dtype=torch.int32, device=dev)
 
     main = torch.cuda.current_stream()
-    pyr = _Pyramid(main, [side_stream, search_stream])
+    pyr = _Pyramid(main, [side_stream, search_stream, transpose_stream])
     flags = pyr.flags
     for st in pyr.streams:
         st.wait_stream(main)             # fork: the inputs were written on the main stream
@@ -130,7 +131,14 @@ def collate_static(pts0, pts1, feat0, feat1, corr, dist_keypts, config, limits, 
     def search(q, s, ql, sl, r, limit, pad, transpose=False):
         idx, info = ops.radius_neighbors_raw(q, s, ql, sl, r, int(limit), torch.int32, None, False, pad_index=pad)
         if transpose:   # training: "which queries list support j", consumed by every KPConv backward over this matrix
-            idx._d3f_transpose = ops.neighbors_transpose(idx, s.shape[0])
+            if transpose_stream is not None:
+                done = torch.cuda.Event()
+                done.record(torch.cuda.current_stream())
+                with torch.cuda.stream(transpose_stream):
+                    transpose_stream.wait_event(done)
+                    idx._d3f_transpose = ops.neighbors_transpose(idx, s.shape[0])
+            else:
+                idx._d3f_transpose = ops.neighbors_transpose(idx, s.shape[0])
         flags.append(info[1:2])           # 1 = a row overflowed the candidate buffer
         # the reference's matrix has min(max_count, limit) columns (dataloader.py:64-65): a row that fills it holds
         # no shadow index, which max_pool / the eval-mode detection gate can see -> keep that width on the device
@@ -218,7 +226,8 @@ class PairStep:
         self.features = None        # [caps[0], 32] descriptors / [caps[0], 1] scores of the last step (static buffers)
         self.scores = None
         self.side_stream = torch.cuda.Stream(device=dev)     # grid-subsampling chain
-        self.search_stream = torch.cuda.Stream(device=dev)   # radius searches + transposed lists; the network consumes
+        self.transpose_stream = torch.cuda.Stream(device=dev)   # transposed neighbour lists (backward only)
+        self.search_stream = torch.cuda.Stream(device=dev)   # radius searches; the network consumes
                                                              # each level as soon as it is ready (see collate_static)
         if self.flat_sgd is not None and cross_fragment is not None and hasattr(model, "_early_block"):
             # data parallel: all-reduce the first gradient bucket while the shallow levels still back-propagate
@@ -245,7 +254,8 @@ class PairStep:
         if self.flat_sgd is not None:
             self.flat_sgd.zero_grad()     # one fill, while the main stream would otherwise wait for the first search
         batch, pyramid = collate_static(*self.inputs, cfg, self.limits, self.caps, self.lengths0, self.side_stream,
-                                        transposes=self.optimizer is not None, search_stream=self.search_stream)
+                                        transposes=self.optimizer is not None, search_stream=self.search_stream,
+                                        transpose_stream=self.transpose_stream)
         feats, scores = self.model(batch)
         status = pyramid.join()          # the backward pass reads the transposed lists built on the search stream
         c = batch['corr']

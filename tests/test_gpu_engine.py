@@ -62,7 +62,8 @@ def test_collate_static_side_streams_same_pyramid(cuda):
     ref, pyr = collate_static(*dev, cfg, limits, [3000, 1280, 384, 128, 64])
     pyr.join()
     s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
-    got, pyr2 = collate_static(*dev, cfg, limits, [3000, 1280, 384, 128, 64], side_stream=s1, transposes=True, search_stream=s2)
+    got, pyr2 = collate_static(*dev, cfg, limits, [3000, 1280, 384, 128, 64], side_stream=s1, transposes=True, search_stream=s2,
+                               transpose_stream=torch.cuda.Stream())
     status = pyr2.join()
     torch.cuda.synchronize()
     assert int(status.abs().sum()) == 0

@@ -59,3 +59,10 @@ for b in range(nb):
         if f > s: acc[short(e["name"])] = acc.get(short(e["name"]), 0.0) + (f - s)
     top = sorted(acc.items(), key=lambda t: -t[1])[:4]
     print("%5.2f ms | occupancy %.2f |" % (b * bucket / 1e3, sum(acc.values()) / bucket), "; ".join("%s %.0f" % (k, v) for k, v in top))
+out = os.path.join(ROOT, "gpurun_out", "step_events.tsv")
+os.makedirs(os.path.dirname(out), exist_ok=True)
+with open(out, "w") as f:
+    for e in ev:
+        a = e.get("args", {})
+        f.write("%.1f\t%.1f\t%s\t%s\t%s\n" % (e["ts"] - t0, e["dur"], a.get("stream", "?"), a.get("grid", ""), short(e["name"])))
+print("wrote", out)
