@@ -196,7 +196,9 @@ extern "C" int d3f_kpconv_backward_ex(const float* q_pts, const float* s_pts, co
     int rc = kp_check(nq, ns, H, K, cin, cout);
     if (rc) return rc;
     D3F_REQUIRE(influence >= 0 && influence <= 2 && aggregation >= 0 && aggregation <= 1, D3F_ERR_INVALID, "bad mode");
-    const bool transposed = (grad_x || grad_weights) && t_offsets && t_src && !deformed && !modulations &&
+    // (a layer whose input needs no gradient -- the first one -- and that kept wf takes the single wf^T g GEMM below: the
+    // gather over the lists plus G^T x cost 195 us at the tail of the step for the 960 weights of the 1 -> 64 layer)
+    const bool transposed = (grad_x || (grad_weights && !wf)) && t_offsets && t_src && !deformed && !modulations &&
                             kp2t_supported(nq, cout) && ns > 0 && nq > 0 && (cout & 3) == 0;
     // the scatter accumulates into grad_x with reductions; the transposed path's GEMM overwrites it
     if (grad_x && ns > 0 && !transposed)
