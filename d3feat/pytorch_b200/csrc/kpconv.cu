@@ -198,7 +198,7 @@ extern "C" int d3f_kpconv_backward_ex(const float* q_pts, const float* s_pts, co
     D3F_REQUIRE(influence >= 0 && influence <= 2 && aggregation >= 0 && aggregation <= 1, D3F_ERR_INVALID, "bad mode");
     // (a layer whose input needs no gradient -- the first one -- and that kept wf takes the single wf^T g GEMM below: the
     // gather over the lists plus G^T x cost 195 us at the tail of the step for the 960 weights of the 1 -> 64 layer)
-    const bool transposed = (grad_x || (grad_weights && !wf)) && t_offsets && t_src && !deformed && !modulations &&
+    const bool transposed = (grad_x || (grad_weights && !wf)) && t_offsets && t_src && !modulations &&
                             kp2t_supported(nq, cout) && ns > 0 && nq > 0 && (cout & 3) == 0;
     // the scatter accumulates into grad_x with reductions; the transposed path's GEMM overwrites it
     if (grad_x && ns > 0 && !transposed)
@@ -214,6 +214,7 @@ extern "C" int d3f_kpconv_backward_ex(const float* q_pts, const float* s_pts, co
     D3F_REQUIRE(workspace && need <= workspace_bytes, D3F_ERR_WORKSPACE, "workspace too small");
     const int KC = K * cin;
     const bool need_scatter = grad_x || (deformed && (grad_kernel_points || grad_modulations));
+    float* scatter_gx = grad_x;
     if (transposed) {
         // atomic-free, and wf-free: G[j,k,o] = sum over the queries i that list support j of w * (1/n_i) * g[i,o]
         // (forward-style gather over the transposed lists), then
@@ -223,7 +224,7 @@ extern "C" int d3f_kpconv_backward_ex(const float* q_pts, const float* s_pts, co
         // so the forward (fused kernel) never writes them.
         float* G = w.dwf;
         Kp2tArgs ta{q_pts, s_pts, t_offsets, t_src, grad_out, inv_n, kernel_points, nq, ns, K, cout, kp_extent, influence,
-                    aggregation};
+                    aggregation, deformed ? 1 : 0};
         rc = kp2t_correlate_launch(ta, G, stream);
         if (rc) return rc;
         if (grad_weights) {
@@ -235,18 +236,25 @@ extern "C" int d3f_kpconv_backward_ex(const float* q_pts, const float* s_pts, co
         if (grad_x) {
             D3fGemm g{ns, cin, K * cout, G, K * cout, weights, cout, grad_x, cin, nullptr, nullptr, nullptr, 0, 0.f, 0, nullptr,
                       nullptr, nullptr, 0, cout, (long long)cin * cout};
-            return d3f_gemm_launch(g, false, true, stream);
+            rc = d3f_gemm_launch(g, false, true, stream);
+            if (rc) return rc;
         }
-        return D3F_OK;
+        // deformable layer: the gradient of the deformed kernel points is query-major (every query owns its K points), so
+        // it stays with the dwf GEMM + the scatter kernel below -- WITHOUT that kernel's grad_x reductions (59 M float
+        // atomics onto 344 K addresses at level 3 of BASELINE config 4: 0.85 ms per layer).  G (in w.dwf) has been
+        // consumed by the GEMMs queued above on this stream.
+        if (!(deformed && grad_kernel_points)) return D3F_OK;
+        scatter_gx = nullptr;
+    } else {
+        D3F_REQUIRE(wf, D3F_ERR_INVALID, "wf is required without transposed neighbour lists");
+        // dW[kc, o] = sum_i wf[i, kc] * inv_n[i] * g[i, o]
+        if (grad_weights) {
+            D3fGemm g{KC, cout, nq, wf, KC, grad_out, cout, grad_weights, cout, nullptr, inv_n, nullptr, 0, 0.f, 0, nullptr};
+            rc = d3f_gemm_launch(g, true, false, stream);
+            if (rc) return rc;
+        }
+        if (!need_scatter) return D3F_OK;
     }
-    D3F_REQUIRE(wf, D3F_ERR_INVALID, "wf is required without transposed neighbour lists");
-    // dW[kc, o] = sum_i wf[i, kc] * inv_n[i] * g[i, o]
-    if (grad_weights) {
-        D3fGemm g{KC, cout, nq, wf, KC, grad_out, cout, grad_weights, cout, nullptr, inv_n, nullptr, 0, 0.f, 0, nullptr};
-        rc = d3f_gemm_launch(g, true, false, stream);
-        if (rc) return rc;
-    }
-    if (!need_scatter) return D3F_OK;
     // dwf[i, kc] = inv_n[i] * sum_o g[i, o] * W[kc, o]
     {
         D3fGemm g{nq, KC, cout, grad_out, cout, weights, cout, w.dwf, KC, inv_n, nullptr, nullptr, 0, 0.f, 0, nullptr};
@@ -260,7 +268,7 @@ extern "C" int d3f_kpconv_backward_ex(const float* q_pts, const float* s_pts, co
     D3F_REQUIRE((long long)ns * cin < (1LL << 31), D3F_ERR_UNSUPPORTED, "Ns * Cin must stay below 2^31");
     Kp2Args a2{q_pts, s_pts, inds, (long long)ld_inds, x, kernel_points, modulations, w.rowpos,
                nq, ns, H, K, cin, kp_extent, influence, aggregation, idx_is_64 ? 1 : 0, deformed ? 1 : 0};
-    return kp2_scatter_launch(a2, w.dwf, wf_unmod, grad_x, deformed ? grad_kernel_points : nullptr,
+    return kp2_scatter_launch(a2, w.dwf, wf_unmod, scatter_gx, deformed ? grad_kernel_points : nullptr,
                               deformed ? grad_modulations : nullptr, stream);
 }
 

@@ -21,6 +21,7 @@ bool kp2_supported(int H, int ns, int cin);
 struct Kp2tArgs {
     const float* q; const float* s; const int* t_off; const int* t_src; const float* g; const float* inv_n;
     const float* kp; int nq, ns, K, cout; float extent; int influence, aggregation;
+    int deformed;   // kp is per query [nq, K, 3] (deformed kernel points) and the in-range filter of blocks.py:300-324 applies
 };
 bool kp2t_supported(int nq, int cout);
 // G [ns, K, cout] = sum over listing queries of w * inv_n * grad_out rows

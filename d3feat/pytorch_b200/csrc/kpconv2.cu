@@ -451,6 +451,107 @@ kp2_scatter_kernel(Kp2Args a, int HP, const float* __restrict__ dwf, const float
     }
 }
 
+// ------------------------------------------------------------------------------------------------ backward, kernel points
+// grad_kernel_points of a deformable (unmodulated) layer on the tensor path:
+//   T[k, h] = sum_c dwf[qi, k, c] * x[idx[h], c]                     one [16 x Cin] x [Cin x 8] mma chain per 8 neighbours
+//   dkp[qi, k, :] = sum_h T[k, h] * dw/dsq(h, k) * (-2) * (rel[h] - kp[k])
+// The scatter kernel above computes the same sums with the lanes over CHANNELS, so all 32 lanes repeat the geometry of
+// every (neighbour, kernel point) pair: 1.05 ms per layer at level 3 of BASELINE config 4 (1344 queries x 173 neighbours
+// x 256 channels), three quarters of that step's backward.  Here the contraction over channels is 3xTF32 mma.sync and a
+// lane evaluates the geometry of the 4 (k, h) pairs its accumulator fragment holds.  Cin % 32 == 0.
+template <bool IDX64>
+__global__ void __launch_bounds__(256)
+kp2_gradkp_kernel(Kp2Args a, int HP, const float* __restrict__ dwf, float* __restrict__ grad_kp) {
+    extern __shared__ float4 smem_f4[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qi = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (qi >= a.nq) return;
+    Kp2Warp wp;
+    kp2_slab(wp, (float*)smem_f4, warp, HP);
+    kp2_phases<IDX64, true>(a, qi, lane, HP, wp, true);     // w_s, rec_s, idx_s (kept neighbours only), kp_s
+    const int cin = a.cin, gq = lane >> 2, tq = lane & 3;
+    const float* __restrict__ D0 = dwf + ((size_t)qi * a.K + gq) * cin + 4 * tq;                 // kernel point gq
+    const bool k1 = gq + 8 < a.K;
+    const float* __restrict__ D1 = dwf + ((size_t)qi * a.K + (k1 ? gq + 8 : gq)) * cin + 4 * tq;  // kernel point gq + 8
+    const float* __restrict__ x = a.x + 4 * tq;
+    float g0[3] = {0.f, 0.f, 0.f}, g1[3] = {0.f, 0.f, 0.f};
+    const int nblk = (wp.hend + 7) >> 3;
+    constexpr int GB = 6;                                   // 8-neighbour blocks per pass: 24 accumulator registers
+    for (int hb0 = 0; hb0 < nblk; hb0 += GB) {
+        float acc[GB][4];
+        unsigned row[GB];
+#pragma unroll
+        for (int b = 0; b < GB; ++b) {
+            acc[b][0] = acc[b][1] = acc[b][2] = acc[b][3] = 0.f;
+            const int id = hb0 + b < nblk ? wp.idx_s[(hb0 + b) * 8 + gq] : -1;
+            row[b] = (unsigned)max(id, 0) * (unsigned)cin;  // dropped neighbours read row 0; their T is never used
+        }
+        for (int c0 = 0; c0 < cin; c0 += 32) {
+            // mma k index <-> channel: step s covers channels c0 + 4 tq + s (k = tq) and c0 + 16 + 4 tq + s (k = tq + 4)
+            const float4 d0 = __ldg((const float4*)(D0 + c0)), d2 = __ldg((const float4*)(D0 + c0 + 16));
+            float4 d1 = make_float4(0.f, 0.f, 0.f, 0.f), d3 = d1;
+            if (k1) { d1 = __ldg((const float4*)(D1 + c0)); d3 = __ldg((const float4*)(D1 + c0 + 16)); }
+            const float da[4][4] = {{d0.x, d1.x, d2.x, d3.x}, {d0.y, d1.y, d2.y, d3.y}, {d0.z, d1.z, d2.z, d3.z},
+                                    {d0.w, d1.w, d2.w, d3.w}};
+            uint32_t ah[4][4], al[4][4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split_tf32(da[s][e], ah[s][e], al[s][e]);
+#pragma unroll
+            for (int b = 0; b < GB; ++b) {
+                if (hb0 + b >= nblk) break;                 // warp-uniform
+                const float4 xa = __ldg((const float4*)(x + row[b] + c0));
+                const float4 xb = __ldg((const float4*)(x + row[b] + c0 + 16));
+                const float va[4] = {xa.x, xa.y, xa.z, xa.w}, vb[4] = {xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    uint32_t bh[2], bl[2];
+                    split_tf32(va[s], bh[0], bl[0]);
+                    split_tf32(vb[s], bh[1], bl[1]);
+                    mma_tf32(acc[b], al[s], bh);
+                    mma_tf32(acc[b], ah[s], bl);
+                    mma_tf32(acc[b], ah[s], bh);
+                }
+            }
+        }
+        // accumulator fragment: acc[b][2 * half + e] = T[k = gq + 8 * half][h = 8 * (hb0 + b) + 2 * tq + e]
+#pragma unroll
+        for (int b = 0; b < GB; ++b) {
+            if (hb0 + b >= nblk) break;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int h = (hb0 + b) * 8 + 2 * tq + e;
+                if (wp.idx_s[h] < 0) continue;
+                const float4 r = wp.rec_s[h];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int k = gq + 8 * half;
+                    if (k >= a.K) continue;
+                    const float dx = r.x - wp.kp_s[3 * k], dy = r.y - wp.kp_s[3 * k + 1], dz = r.z - wp.kp_s[3 * k + 2];
+                    const float sq = dx * dx + dy * dy + dz * dz;
+                    const float w = wp.w_s[h * WS + k];
+                    float gw = kp2_influence_grad(sq, w, a.extent, a.influence);
+                    if (a.aggregation == D3F_AGGREGATION_CLOSEST && w == 0.f) gw = 0.f;   // w_s is zero off the closest point
+                    const float f = acc[b][2 * half + e] * gw * (-2.0f);
+                    float* g = half ? g1 : g0;
+                    g[0] = fmaf(f, dx, g[0]); g[1] = fmaf(f, dy, g[1]); g[2] = fmaf(f, dz, g[2]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+        float v0 = g0[ax], v1 = g1[ax];
+        v0 += __shfl_xor_sync(FULL, v0, 1); v0 += __shfl_xor_sync(FULL, v0, 2);
+        v1 += __shfl_xor_sync(FULL, v1, 1); v1 += __shfl_xor_sync(FULL, v1, 2);
+        if (tq == 0) {
+            if (gq < a.K) grad_kp[((size_t)qi * a.K + gq) * 3 + ax] = v0;
+            if (k1) grad_kp[((size_t)qi * a.K + gq + 8) * 3 + ax] = v1;
+        }
+    }
+}
+
 // Rigid layers with Cin a multiple of 32 (<= 128 per pass): a lane owns 4 consecutive channels, VL = 8*CV lanes cover
 // a 32*CV-channel row, and the warp's 32/VL lane groups take different neighbours, so one step reads the weights of
 // 32/VL neighbours with 4 LDS.128 and issues ONE vector reduction (16 bytes per lane).
@@ -503,7 +604,9 @@ kp2_scatter_vec_kernel(Kp2Args a, int HP, const float* __restrict__ dwf, float* 
 // G[j, k, o] = sum over the queries i that list support j of  w[i, k, h(i,j)] * inv_n[i] * g[i, o]
 // -- the forward gather over the TRANSPOSED neighbour lists (t_off / t_src, transpose.cu), reading rows of the output
 // gradient instead of rows of x.  dx = G [Ns, K*Cout] x W^T then is one GEMM (kpconv.cu).  One warp per support point,
-// lists walked in chunks of HT entries with the accumulators kept in registers; rigid layers, Cout % 32 == 0.
+// lists walked in chunks of HT entries with the accumulators kept in registers; Cout % 32 == 0.  Deformable layers read
+// the listing query's own kernel points per entry (the gradient of those points is query-major and stays with the
+// scatter kernel, which then skips its grad_x reductions).
 constexpr int HT = 64;
 __host__ __device__ inline size_t kp2t_warp_floats() { return (size_t)HT * (WS + 5); }   // w_s | rec_s (float4) | idx_s
 
@@ -522,8 +625,8 @@ kp2t_correlate_kernel(Kp2tArgs a, float* __restrict__ G) {
     const int k = lane & 15, hh = lane >> 4;
     const bool kvalid = k < a.K;
     float kx = 0.f, ky = 0.f, kz = 0.f;
-    if (kvalid) { kx = a.kp[3 * k]; ky = a.kp[3 * k + 1]; kz = a.kp[3 * k + 2]; }
-    const float inv_ext = 1.0f / a.extent;
+    if (kvalid && !a.deformed) { kx = a.kp[3 * k]; ky = a.kp[3 * k + 1]; kz = a.kp[3 * k + 2]; }
+    const float inv_ext = 1.0f / a.extent, ext2 = a.extent * a.extent;
     const float sigma = a.extent * 0.3f, gden = 2.0f * sigma * sigma + 1e-9f;
     const int gq = lane >> 2, tq = lane & 3;
     const int cout = a.cout;
@@ -561,6 +664,13 @@ kp2t_correlate_kernel(Kp2tArgs a, float* __restrict__ G) {
             for (int t = 0; t < (cnt8 >> 1); ++t) {
                 const int h = 2 * t + hh;
                 const float4 r = rec_s[h];
+                if (a.deformed) {      // the listing query's own (deformed) kernel points, blocks.py:286-291
+                    const int i = idx_s[h];
+                    if (kvalid && i >= 0) {
+                        const float* p = a.kp + ((size_t)i * a.K + k) * 3;
+                        kx = p[0]; ky = p[1]; kz = p[2];
+                    }
+                }
                 const float dx = r.x - kx, dy = r.y - ky, dz = r.z - kz;
                 const float sq = dx * dx + dy * dy + dz * dz;
                 float w;
@@ -577,6 +687,10 @@ kp2t_correlate_kernel(Kp2tArgs a, float* __restrict__ G) {
                         if (os < bs || (os == bs && ok < bk)) { bs = os; bk = ok; }
                     }
                     if (bk != k) w = 0.f;
+                }
+                if (a.deformed) {      // blocks.py:300-324: the pair counts only inside some kernel point's extent
+                    const unsigned b = __ballot_sync(FULL, kvalid && sq < ext2);
+                    if (((b >> (hh * 16)) & 0xFFFFu) == 0) w = 0.f;
                 }
                 w_s[h * WS + k] = kvalid ? w * r.w : 0.f;      // r.w = 0 for the padding entries
             }
@@ -747,6 +861,21 @@ int kp2_scatter_launch(const Kp2Args& a, const float* dwf, const float* wf_unmod
                      (a.cin == 32 || a.cin == 64 || (a.cin & 127) == 0) && (((size_t)dwf | (size_t)grad_x) & 15) == 0;
     if (vec) return a.idx64 ? scatter_vec<true>(a, HP, grid, warps, smem, dwf, grad_x, stream)
                             : scatter_vec<false>(a, HP, grid, warps, smem, dwf, grad_x, stream);
+    // kernel-point gradient alone (the data gradient came from the transposed lists): tensor-path kernel
+    if (a.deformed && !grad_x && grad_kp && !grad_mod && !a.mod && (a.cin & 31) == 0 &&
+        (((size_t)dwf | (size_t)a.x) & 15) == 0) {
+        if (a.idx64) {
+            int rc_ = kp2_set_smem(kp2_gradkp_kernel<true>, smem);
+            if (rc_) return rc_;
+            kp2_gradkp_kernel<true><<<grid, warps * 32, smem, stream>>>(a, HP, dwf, grad_kp);
+        } else {
+            int rc_ = kp2_set_smem(kp2_gradkp_kernel<false>, smem);
+            if (rc_) return rc_;
+            kp2_gradkp_kernel<false><<<grid, warps * 32, smem, stream>>>(a, HP, dwf, grad_kp);
+        }
+        D3F_CHECK_LAUNCH();
+        return D3F_OK;
+    }
     if (a.idx64) {
         if (a.deformed) return scatter_cg<true, true>(a, HP, grid, warps, smem, dwf, wf_unmod, grad_x, grad_kp, grad_mod, stream);
         return scatter_cg<true, false>(a, HP, grid, warps, smem, dwf, wf_unmod, grad_x, grad_kp, grad_mod, stream);

@@ -155,14 +155,14 @@ def collate_static(pts0, pts1, feat0, feat1, corr, dist_keypts, config, limits, 
             pyr.wait(('points', l))                      # (no-op for level 0 and without a side stream)
             if has_conv:
                 r = r_normal * config.deform_radius / config.conv_radius if deform_conv else r_normal
-                conv_i = search(pts[l], pts[l], lens[l], lens[l], r, limits[l], cap, transposes and not deform_conv)
+                conv_i = search(pts[l], pts[l], lens[l], lens[l], r, limits[l], cap, transposes)
                 pyr.mark(('neighbors', l), search_stream)
             else:
                 conv_i = empty_idx
             if has_pool:
                 pyr.wait(('points', l + 1))
                 r = r_normal * config.deform_radius / config.conv_radius if deform_pool else r_normal
-                pool_i = search(pts[l + 1], pts[l], lens[l + 1], lens[l], r, limits[l], cap, transposes and not deform_pool)
+                pool_i = search(pts[l + 1], pts[l], lens[l + 1], lens[l], r, limits[l], cap, transposes)
                 pyr.mark(('pools', l), search_stream)
                 up_i = None     # only the decoder reads the upsampling matrices: searched after every encoder matrix
                 deferred.append((l, 2 * r))

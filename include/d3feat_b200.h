@@ -154,10 +154,12 @@ int d3f_kpconv_backward(const float* q_pts, const float* s_pts, const void* inds
 /* Transposed neighbour lists for the atomic-free backward: for every support j the queries i with inds[i, h] = j
  * (any h), as CSR:  t_offsets [n_supports + 1] i32,  t_src [n_queries * n_neighbors capacity] i32 (query indices in
  * ascending order inside a list, so the backward that sums in list order is bit-reproducible).  One call per neighbour matrix; every KPConv layer that uses the matrix shares it.
- * d3f_kpconv_backward_ex = d3f_kpconv_backward plus (t_offsets, t_src): when both are given and the layer is rigid with
- * Cout % 32 == 0, grad_x is computed as a forward-style gather over the lists followed by one GEMM with W^T -- no float
- * atomics (the 45 M reductions of level 0 cost 200 us however they are issued) and a deterministic result per list order;
- * otherwise it falls back to the scatter of d3f_kpconv_backward.  The KPConv workspace covers both. */
+ * d3f_kpconv_backward_ex = d3f_kpconv_backward plus (t_offsets, t_src): when both are given and the layer is unmodulated
+ * with Cout % 32 == 0, grad_x is computed as a forward-style gather over the lists followed by one GEMM with W^T -- no float
+ * atomics (the 45 M reductions of level 0 cost 200 us however they are issued) and a deterministic result per list order.
+ * Deformable layers (kernel_points [Nq,K,3]) take the same path with each listing query's own kernel points; their
+ * grad_kernel_points (query-major) still comes from the scatter kernel, which then issues no grad_x reductions.
+ * Otherwise it falls back to the scatter of d3f_kpconv_backward.  The KPConv workspace covers both. */
 size_t d3f_neighbors_transpose_workspace_bytes(int n_supports);
 int d3f_neighbors_transpose(const void* inds, int idx_is_64, int64_t ld_inds, int n_queries, int n_supports,
                             int n_neighbors, int32_t* t_offsets, int32_t* t_src, void* workspace, size_t workspace_bytes,

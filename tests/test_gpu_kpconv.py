@@ -222,3 +222,41 @@ def test_transposed_lists_are_sorted_and_backward_is_reproducible(cuda):
             assert np.array_equal(seg, np.nonzero((inds.cpu().numpy() == j).any(1))[0])
         again = ops.neighbors_transpose(inds, ns)
         assert torch.equal(again[0], t_off) and torch.equal(again[1][:off[-1]], t_src[:off[-1]])
+
+
+@pytest.mark.parametrize("nq,ns,H,cin,cout,infl", [(300, 300, 60, 64, 64, "linear"), (90, 90, 151, 128, 32, "linear"),
+                                                   (200, 150, 40, 32, 64, "gaussian")])
+def test_deformable_backward_over_transposed_lists(cuda, nq, ns, H, cin, cout, infl):
+    """Deformable layer (per-query kernel points + the in-range neighbour filter of blocks.py:300-324): grad_x through the
+    gather over the transposed lists, grad_kernel_points from the scatter kernel without its grad_x reductions -- against
+    the CPU oracle (autograd through oracle.model_ref.kpconv_rigid(kp_per_query=...)) and against the all-scatter path."""
+    from oracle import model_ref
+    from d3feat.pytorch_b200 import ops
+    from d3feat.pytorch_b200.blocks import _KPConvFunction
+    rng = np.random.default_rng(nq + H)
+    q = torch.from_numpy((rng.random((nq, 3)) * 0.2).astype(np.float32))
+    s = q.clone() if ns == nq else torch.from_numpy((rng.random((ns, 3)) * 0.2).astype(np.float32))
+    inds = torch.from_numpy(rng.integers(0, ns + 1, size=(nq, H)).astype(np.int64))      # ns = shadow
+    x = torch.from_numpy(rng.standard_normal((ns, cin)).astype(np.float32)).requires_grad_(True)
+    W = torch.from_numpy((rng.standard_normal((15, cin, cout)) / np.sqrt(15 * cin)).astype(np.float32)).requires_grad_(True)
+    kp0 = (_inputs.unit_kernel_points() * 0.075).astype(np.float32)
+    kpd = torch.from_numpy(kp0[None] + 0.01 * rng.standard_normal((nq, 15, 3)).astype(np.float32)).requires_grad_(True)
+    gout = torch.from_numpy(rng.standard_normal((nq, cout)).astype(np.float32))
+    ref = model_ref.kpconv_rigid(q, s, inds, x, W, torch.from_numpy(kp0), 0.06, influence=infl, kp_per_query=kpd)
+    (ref * gout).sum().backward()
+    inds_g = inds.to(cuda).to(torch.int32)
+    lists = ops.neighbors_transpose(inds_g, ns)
+    grads = []
+    for tr in ((None, None), lists):
+        xg = x.detach().to(cuda).requires_grad_(True)
+        Wg = W.detach().to(cuda).requires_grad_(True)
+        kg = kpd.detach().to(cuda).requires_grad_(True)
+        out, _ = _KPConvFunction.apply(q.to(cuda), s.to(cuda), inds_g, xg, Wg, kg, None, 0.06, infl, "sum",
+                                       True, False, None, None, tr[0], tr[1])
+        assert rel_err(out.detach().cpu(), ref.detach()) < TOL
+        (out * gout.to(cuda)).sum().backward()
+        grads.append((xg.grad.cpu(), Wg.grad.cpu(), kg.grad.cpu()))
+    for got, want, name in zip(grads[1], (x.grad, W.grad, kpd.grad), ("x", "W", "kp")):
+        assert rel_err(got, want) < TOL, name
+    for a, b in zip(grads[1], grads[0]):
+        assert rel_err(a, b) < 2e-5

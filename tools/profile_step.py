@@ -1,4 +1,5 @@
-"""Kernel-time table of the CUDA-graph pair step (torch.profiler / CUPTI): python tools/profile_step.py [n_points]"""
+"""Kernel-time table of the CUDA-graph pair step (torch.profiler / CUPTI): python tools/profile_step.py [n_points] [deform]
+(`deform`: BASELINE config 4 architecture -- deformable KPConv from level 3)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -13,7 +14,11 @@ from d3feat.pytorch_b200.loss import PairLoss
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 torch.cuda.set_device(0); dev = torch.device("cuda:0")
-cfg = default_config(); torch.manual_seed(0); np.random.seed(0)
+cfg = default_config()
+if len(sys.argv) > 2 and sys.argv[2] == "deform":
+    from d3feat.pytorch_b200.config import build_architecture
+    cfg = default_config(architecture=build_architecture(5, deformable_from=3))
+torch.manual_seed(0); np.random.seed(0)
 model = KPFCNN(cfg).to(dev); model.train()
 from d3feat.pytorch_b200.optim import FlatSGD
 opt = FlatSGD(model, lr=0.01, momentum=0.98, weight_decay=1e-6)
