@@ -72,10 +72,10 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* fa
     return false;
 }
 
+// tf32 "hi" part.  cvt.rna.tf32 is emulated on sm_100a (FSETP + IADD + LOP3): round to nearest by hand (add half an ulp
+// of the 10-bit mantissa, clear 13 bits; inputs are finite).  hi + (v - hi) == v exactly either way.
 __device__ __forceinline__ float tf32_hi(float v) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
 }
 
 __device__ __forceinline__ float4 ld4g(const float* __restrict__ p, int valid, bool vec) {
@@ -141,7 +141,49 @@ tc5_gemm_kernel(D3fGemm g) {
     const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
     float4 ra[4], rb[BN >= 128 ? BN / 32 : 4];
+    // Interior tiles (a full BK of K, 16-byte aligned operands, full M / N tile where the operand is transposed): every
+    // thread's loads sit at a fixed offset from a base that advances by one tile per iteration, so the 64-bit address
+    // and bounds arithmetic of the generic path below (~900 cycles per tile for the single warp that also issues the
+    // MMAs) is done once.  The generic path still takes the last partial tile and unaligned / scaled operands.
+    const bool fast = a_vec && b_vec && !g.ks && (!g.bblk || ((g.bblk % BK) == 0 && (g.bblk_stride & 3) == 0)) && (!TA || m0 + BM <= g.M) &&
+                      (TB || n0 + BN <= g.N);
+    const float* ap0;
+    const float* bp0;
+    size_t a_rs, b_rs, a_step, b_step;
+    uint32_t amask = 0, bmask = 0;
+    if (!TA) {
+        ap0 = g.A + (size_t)(m0 + (tid >> 3)) * g.lda + kbeg + (tid & 7) * 4;
+        a_rs = (size_t)32 * g.lda; a_step = BK;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) amask |= (m0 + (tid >> 3) + 32 * r < g.M ? 1u : 0u) << r;
+    } else {
+        ap0 = g.A + (size_t)(kbeg + (tid >> 5) * 4) * g.lda + m0 + (tid & 31) * 4;
+        a_rs = (size_t)g.lda; a_step = (size_t)BK * g.lda; amask = 0xFu;
+    }
+    if (TB) {
+        bp0 = g.B + (size_t)(n0 + (tid >> 3)) * g.ldb + (tid & 7) * 4;      // + the tile's k offset (block-wise B: per tile)
+        b_rs = (size_t)32 * g.ldb; b_step = BK;
+#pragma unroll
+        for (int r = 0; r < BN / 32; ++r) bmask |= (n0 + (tid >> 3) + 32 * r < g.N ? 1u : 0u) << r;
+    } else {
+        bp0 = g.B + (size_t)(kbeg + (tid / (BN / 4)) * 4) * g.ldb + n0 + (tid % (BN / 4)) * 4;
+        b_rs = (size_t)g.ldb; b_step = (size_t)BK * g.ldb; bmask = tid < 2 * BN ? 0xFu : 0u;
+    }
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     auto load_tile = [&](int k0) {
+        if (fast && k0 + BK <= kend) {
+            const size_t t = (size_t)((k0 - kbeg) / BK);
+            const float* ap = ap0 + t * a_step;
+            const float* bp;
+            if (TB) bp = bp0 + (g.bblk ? (size_t)(k0 / g.bblk) * g.bblk_stride + (size_t)(k0 % g.bblk) : (size_t)k0);
+            else bp = bp0 + t * b_step;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) ra[r] = (amask >> r) & 1u ? __ldg((const float4*)(ap + r * a_rs)) : zero4;
+#pragma unroll
+            for (int r = 0; r < (TB ? BN / 32 : 4); ++r)
+                rb[r] = (bmask >> r) & 1u ? __ldg((const float4*)(bp + r * b_rs)) : zero4;
+            return;
+        }
         if (!TA) {      // A[m][k]: thread = (row, 16-byte k unit)
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
@@ -224,8 +266,6 @@ tc5_gemm_kernel(D3fGemm g) {
         TC5_T(0);
         store_tile();
         TC5_T(1);
-        if (kt + 1 < nk) load_tile(kbeg + (kt + 1) * BK);                          // global loads overlap the MMAs
-        TC5_T(2);
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");              // generic-proxy stores -> async proxy (UMMA)
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
         TC5_T(3);
@@ -257,6 +297,10 @@ tc5_gemm_kernel(D3fGemm g) {
                          :: "r"(smem_u32(&bars[0])) : "memory");
         }
         TC5_T(5);
+        // the next tile's global loads are issued AFTER the MMAs (they used to sit between the stores and the barrier,
+        // delaying every MMA issue by their address arithmetic): they now overlap the tensor core's work on this tile
+        if (kt + 1 < nk) load_tile(kbeg + (kt + 1) * BK);
+        TC5_T(2);
     }
 
     // ---- epilogue
