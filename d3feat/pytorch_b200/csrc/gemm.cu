@@ -290,12 +290,16 @@ int d3f_gemm_launch(const D3fGemm& in, bool ta, bool tb, cudaStream_t stream, fl
         }
     } else {
         if (g.K > 0 && plain) {
-            // atomically combined partials.  Fitted to the sweep of tools/gemm_tune.py over every GEMM of the step
-            // (profiles/r2_gemm_tune.txt): about two CTAs per SM in flight (more splits only add atomics and a zero
-            // fill: [13312 x 128 x 256] ran 36 us split in three, 25 us unsplit), never more than 16 K tiles in one
-            // CTA's serial loop ([256 x 768 x 13312]: 77 us at 12 splits, 60 us at 24), at least 2 K tiles per split.
+            // atomically combined partials.  Fitted to the sweeps of tools/gemm_tune.py over every GEMM of the step
+            // (profiles/r2_gemm_tune*.txt, re-fitted after the K loop got faster): fill the SMs first (splitting is free
+            // while CTAs < SMs: [256 x 1024 x 512] 25 us unsplit, 15 us in four); beyond that a split costs ~4-7 us of
+            // reductions (+ a zero fill outside engine.PairStep's arena) and pays only while a CTA keeps >= 8 K tiles
+            // ([768 x 1024 x 256], 96 tiles x 8 K tiles: 17 us unsplit, 21 us in three); never more than 32 K tiles in one
+            // CTA's serial loop ([256 x 768 x 13312]: 144 us in three, 58 us in twelve).
             const int kt = d3f_ceil_div(g.K, BK);
-            splits = max(296 / tiles, d3f_ceil_div(kt, 16));
+            splits = min(148 / tiles, kt / 2);
+            splits = max(splits, min(296 / tiles, kt / 8));
+            splits = max(splits, d3f_ceil_div(kt, 32));
             splits = min(splits, kt / 2);
             if (splits < 1) splits = 1;
         }
