@@ -57,6 +57,9 @@ SIGNATURES = {
     "d3f_detection_scores_backward": (c_i, [c_p, c_p, c_i, c_i64, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
     "d3f_det_loss_forward": (c_i, [c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p]),
     "d3f_det_loss_backward": (c_i, [c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p]),
+    "d3f_exchange_chunk_bytes": (c_sz, [c_i, c_i]),
+    "d3f_exchange_pack": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
+    "d3f_exchange_unpack": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
     "d3f_set_gemm_impl": (None, [c_i]),
     "d3f_set_gemm_tuning": (None, [c_i, c_i]),
     "d3f_gemm_tcgen05_failed": (c_i, []),

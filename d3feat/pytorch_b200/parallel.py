@@ -31,10 +31,62 @@ def _unpack(buf, P, D):
     return a, p, sa, sp, dk
 
 
+class _AttachLocal(torch.autograd.Function):
+    """`gathered` [W*P, ...] holds every rank's rows (constants); rows lo:lo+P are bit-identical copies of `local`.
+    Returns `gathered` attached to the autograd graph of `local`: the gradient of the local slice flows back, the other
+    ranks' rows stay constants (what torch.cat of [const..., local, const...] did, without the W+1 kernels)."""
+
+    @staticmethod
+    def forward(ctx, local, gathered, lo):
+        ctx.lo, ctx.shape = lo, local.shape
+        ctx.mark_dirty(gathered)
+        return gathered
+
+    @staticmethod
+    def backward(ctx, g):
+        n = ctx.shape[0]
+        return g[ctx.lo:ctx.lo + n].reshape(ctx.shape), None, None
+
+
+def _gather_pairs_cuda(a, p, sa, sp, dk, group):
+    """gather_pairs on the GPU: ONE pack kernel, ONE all-gather, ONE unpack kernel (csrc/exchange.cu)."""
+    from . import _lib
+    lib = _lib.load()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    P, D = a.shape
+    dev = a.device
+    st = torch.cuda.current_stream().cuda_stream
+    chunk = int(lib.d3f_exchange_chunk_bytes(P, D))
+    mine = torch.empty(chunk, dtype=torch.uint8, device=dev)
+    af, pf = a.detach().float().contiguous(), p.detach().float().contiguous()
+    saf, spf = sa.detach().float().reshape(-1).contiguous(), sp.detach().float().reshape(-1).contiguous()
+    if dk.dtype not in (torch.float32, torch.float64):
+        dk = dk.double()
+    dkc = dk.detach().contiguous()
+    _lib.check(lib.d3f_exchange_pack(af.data_ptr(), pf.data_ptr(), saf.data_ptr(), spf.data_ptr(), dkc.data_ptr(),
+                                     int(dkc.dtype == torch.float64), P, D, mine.data_ptr(), st))
+    allbuf = torch.empty(world * chunk, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(allbuf, mine, group=group)
+    A = torch.empty((world * P, D), dtype=torch.float32, device=dev)
+    Pos = torch.empty_like(A)
+    SA = torch.empty((world * P, 1), dtype=torch.float32, device=dev)
+    SP = torch.empty_like(SA)
+    DK = torch.empty((world * P, world * P), dtype=torch.float64, device=dev)
+    _lib.check(lib.d3f_exchange_unpack(allbuf.data_ptr(), world, P, D, A.data_ptr(), Pos.data_ptr(), SA.data_ptr(),
+                                       SP.data_ptr(), DK.data_ptr(), st))
+    lo = rank * P
+    attach = lambda local, full: _AttachLocal.apply(local, full, lo) if local.requires_grad else full
+    return (attach(a, A), attach(p, Pos), attach(sa.reshape(P, 1), SA), attach(sp.reshape(P, 1), SP), DK)
+
+
 def gather_pairs(a, p, sa, sp, dk, group=None):
     """All-gather every rank's (anchor, positive, scores, dist_keypts).  The local rank's slices stay
     attached to the autograd graph; the other ranks' slices are constants.
-    Returns (A [W*P,D], Pos [W*P,D], SA [W*P,1], SP [W*P,1], DK [W*P,W*P] f64 block-diagonal, +inf elsewhere)."""
+    Returns (A [W*P,D], Pos [W*P,D], SA [W*P,1], SP [W*P,1], DK [W*P,W*P] f64 block-diagonal, +inf elsewhere).
+    CUDA tensors take the two-kernel path of csrc/exchange.cu; CPU tensors (the gloo tests of the host logic) the
+    torch-op restatement below."""
+    if a.is_cuda and a.dtype == torch.float32 and p.dtype == torch.float32:
+        return _gather_pairs_cuda(a, p, sa, sp, dk, group)
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     P, D = a.shape

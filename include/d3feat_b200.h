@@ -235,6 +235,17 @@ int d3f_det_loss_backward(const float* rowval, const int32_t* arg, const float* 
                           float* grad_pos_score, d3f_stream stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Multi-GPU exchange step (the reference has no multi-GPU code): pack a rank's P selected descriptor
+ * pairs, scores and keypoint distances into ONE chunk for a single all-gather, and unpack W gathered chunks into the
+ * inputs of the (W*P)^2 cross-fragment loss (dist_keypts block-diagonal, +inf between different fragments).
+ * chunk = f32 anchor [P,D] | f32 positive [P,D] | f32 anc_score [P] | f32 pos_score [P] | f64 dist_keypts [P,P]. */
+size_t d3f_exchange_chunk_bytes(int P, int D);
+int d3f_exchange_pack(const float* anchor, const float* positive, const float* anc_score, const float* pos_score,
+                      const void* dist_keypts, int dk_is_f64, int P, int D, void* chunk, d3f_stream stream);
+int d3f_exchange_unpack(const void* all, int W, int P, int D, float* A, float* Pos, float* SA, float* SP,
+                        double* DK, d3f_stream stream);
+
+/* ------------------------------------------------------------------------------------------
  * Gathers between the KPConv layers (they dominate a GPU training step
  * when left to ATen advanced indexing).  Shadow index (>= n_supports) reads a zero row.
  *

@@ -103,3 +103,35 @@ def test_det_loss_on_an_arbitrary_distance_matrix_vs_oracle(cuda, P):
     assert rel_err(Dg.grad.cpu(), D.grad) < TOL
     with pytest.raises(RuntimeError):
         DetLoss()(torch.from_numpy(d), SA, SP)          # CPU tensors: no CPU path
+
+
+@pytest.mark.parametrize("W,P,D,dk_dtype", [(3, 7, 32, torch.float64), (2, 128, 32, torch.float64), (8, 16, 5, torch.float32)])
+def test_exchange_pack_unpack_bit_exact(cuda, W, P, D, dk_dtype):
+    """d3f_exchange_pack / d3f_exchange_unpack (the multi-GPU exchange step around the all-gather): W packed chunks
+    unpack to exactly the rows that went in, with dist_keypts block-diagonal and +inf between different fragments."""
+    from d3feat.pytorch_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(W * 100 + P)
+    st = torch.cuda.current_stream().cuda_stream
+    chunk = int(lib.d3f_exchange_chunk_bytes(P, D))
+    assert chunk == (2 * P * D + 2 * P) * 4 + P * P * 8
+    allbuf = torch.empty(W * chunk, dtype=torch.uint8, device=cuda)
+    parts = []
+    for r in range(W):
+        a, p = torch.randn(P, D, generator=g).to(cuda), torch.randn(P, D, generator=g).to(cuda)
+        sa, sp = torch.rand(P, generator=g).to(cuda), torch.rand(P, generator=g).to(cuda)
+        dk = torch.rand(P, P, generator=g, dtype=torch.float64).to(dk_dtype).to(cuda)
+        parts.append((a, p, sa, sp, dk))
+        _lib.check(lib.d3f_exchange_pack(a.data_ptr(), p.data_ptr(), sa.data_ptr(), sp.data_ptr(), dk.data_ptr(),
+                                         int(dk_dtype == torch.float64), P, D, allbuf[r * chunk:].data_ptr(), st))
+    A = torch.empty(W * P, D, device=cuda); Pos = torch.empty_like(A)
+    SA = torch.empty(W * P, device=cuda); SP = torch.empty_like(SA)
+    DK = torch.empty(W * P, W * P, dtype=torch.float64, device=cuda)
+    _lib.check(lib.d3f_exchange_unpack(allbuf.data_ptr(), W, P, D, A.data_ptr(), Pos.data_ptr(), SA.data_ptr(), SP.data_ptr(),
+                                       DK.data_ptr(), st))
+    want = torch.full((W * P, W * P), float("inf"), dtype=torch.float64, device=cuda)
+    for r, (a, p, sa, sp, dk) in enumerate(parts):
+        want[r * P:(r + 1) * P, r * P:(r + 1) * P] = dk.double()
+    assert torch.equal(A, torch.cat([t[0] for t in parts])) and torch.equal(Pos, torch.cat([t[1] for t in parts]))
+    assert torch.equal(SA, torch.cat([t[2] for t in parts])) and torch.equal(SP, torch.cat([t[3] for t in parts]))
+    assert torch.equal(DK, want)
