@@ -534,7 +534,8 @@ class ZeroArena:
     def reset(self):
         need = self.off + self.spilled
         if self.buf is None or self.buf.numel() < need:
-            self.buf = torch.zeros(need, dtype=torch.float32, device="cuda") if need else None
+            self.buf = (torch.zeros(need, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+                        if need else None)
         elif self.off:
             self.buf[:self.off].zero_()
         self.high, self.off, self.spilled = self.off, 0, 0
