@@ -184,6 +184,21 @@ kp2_correlate_kernel(Kp2Args a, int HP, float* __restrict__ wf, float* __restric
     }
     const float* __restrict__ x = a.x;
     const int cin = a.cin;
+    if (cin == 1 && !a.mod) {
+        // ---- one input channel (the first layer: the reference feeds a constant feature, datasets/ThreeDMatch.py):
+        // wf[qi, k] = sum_h w[k,h] x[idx[h]].  The generic loops below put the lanes over CHANNELS -- one lane of 32 at
+        // work, 96 us for 40000 queries at the head of the forward pass; here the lanes are (neighbour parity, kernel
+        // point), as in phase B.
+        const int k = lane & 15, hh = lane >> 4;
+        float acc = 0.f;
+        for (int h = hh; h < wp.hend; h += 2) {
+            const int idx = wp.idx_s[h];
+            if (idx >= 0) acc = fmaf(wp.w_s[h * WS + k], __ldg(x + idx), acc);
+        }
+        acc += __shfl_xor_sync(FULL, acc, 16);
+        if (lane < a.K) wf[(size_t)qi * a.K + lane] = acc;
+        return;
+    }
     // gridDim.y > 1: one 32*CG-channel chunk per blockIdx.y (deep levels: a few hundred queries x 256-512 channels would
     // otherwise occupy 32-96 CTAs for tens of microseconds of pure latency)
     const int c_lo = gridDim.y > 1 ? (int)blockIdx.y * 32 * CG : 0;
