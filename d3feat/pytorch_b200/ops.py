@@ -525,7 +525,8 @@ class ZeroArena:
     body and calls reset() first; a view is handed out once per step and never reused inside it.  The buffer is sized by
     the previous step (capture() warms up eagerly first); a request that does not fit falls back to torch.zeros."""
 
-    def __init__(self):
+    def __init__(self, device=None):
+        self.device = device  # None: the current CUDA device at the first reset()
         self.buf = None
         self.off = 0          # floats handed out in this step
         self.spilled = 0      # floats that did not fit in this step
@@ -534,8 +535,9 @@ class ZeroArena:
     def reset(self):
         need = self.off + self.spilled
         if self.buf is None or self.buf.numel() < need:
-            self.buf = (torch.zeros(need, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
-                        if need else None)
+            if self.device is None:
+                self.device = torch.device("cuda", torch.cuda.current_device())
+            self.buf = torch.zeros(need, dtype=torch.float32, device=self.device) if need else None
         elif self.off:
             self.buf[:self.off].zero_()
         self.high, self.off, self.spilled = self.off, 0, 0

@@ -45,3 +45,28 @@ def test_bench_byte_accounting_matches_survey():
     assert ns["kpconv_logical_bytes"](40000, 40000, 35, 32, 32) == 207261440
     assert abs(ns["kpconv_flops"](40000, 36, 32, 32) / 1e9 - 2.87) < 0.05
     assert spec is not None
+
+
+def test_zero_arena_sizes_itself_from_the_previous_step_and_hands_out_cleared_views():
+    """ops.ZeroArena (one fill per step for every split-K GEMM output): the first step spills to torch.zeros, reset() then
+    allocates what that step needed, later steps take 128-byte-aligned views of the cleared buffer, a request that does
+    not fit still gets zeros, and reset() clears exactly what was handed out."""
+    import torch
+    from d3feat.pytorch_b200.ops import ZeroArena
+    dev = torch.device("cpu")
+    ar = ZeroArena(dev)
+    ar.reset()
+    a = ar.take(100, dev); b = ar.take(7, dev)
+    assert ar.buf is None and ar.spilled == 128 + 32 and float(a.abs().sum() + b.abs().sum()) == 0.0
+    ar.reset()                                   # sized by the step before: 160 floats
+    assert ar.buf.numel() == 160 and ar.off == 0
+    a = ar.take(100, dev); b = ar.take(7, dev)
+    assert a.data_ptr() == ar.buf.data_ptr() and b.data_ptr() == ar.buf.data_ptr() + 128 * 4 and ar.spilled == 0
+    a.fill_(3.0); b.fill_(5.0)
+    c = ar.take(50, dev)                         # does not fit any more: falls back to fresh zeros
+    assert ar.spilled == 64 and c.data_ptr() != ar.buf.data_ptr() and float(c.abs().sum()) == 0.0
+    ar.reset()                                   # grows to 224 floats (fresh zeros)
+    assert ar.buf.numel() == 224 and float(ar.buf.abs().sum()) == 0.0
+    x = ar.take(224, dev); x.fill_(1.0)
+    ar.reset()                                   # same size: cleared in place
+    assert ar.buf.numel() == 224 and float(ar.buf.abs().sum()) == 0.0 and ar.high == 224

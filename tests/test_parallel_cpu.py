@@ -98,3 +98,21 @@ def test_pack_roundtrip():
     a, p, sa, sp, dk = _inputs(3, P=5, D=32)
     ua, up, usa, usp, udk = _unpack(_pack(a, p, sa, sp, dk), 5, 32)
     assert torch.equal(ua, a) and torch.equal(up, p) and torch.equal(usa, sa) and torch.equal(usp, sp) and torch.equal(udk, dk)
+
+
+def test_attach_local_rows_gradient_is_the_local_slice():
+    """parallel._AttachLocal (the CUDA exchange path's replacement for torch.cat([const.., local, const..])): forward is
+    the gathered matrix itself, backward hands the local rows' gradient to the local tensor and nothing to the rest."""
+    from d3feat.pytorch_b200 import parallel
+    g = torch.Generator().manual_seed(3)
+    local = torch.randn(4, 5, generator=g, requires_grad=True)
+    others = [torch.randn(4, 5, generator=g) for _ in range(2)]
+    w = torch.randn(12, 5, generator=g)
+    want = torch.cat([others[0], local, others[1]])
+    (want * w).sum().backward()
+    ref_grad, local.grad = local.grad.clone(), None
+    gathered = torch.cat([others[0], local.detach(), others[1]])
+    out = parallel._AttachLocal.apply(local, gathered, 4)
+    assert out.requires_grad and torch.equal(out.detach(), want.detach())
+    (out * w).sum().backward()
+    assert torch.equal(local.grad, ref_grad)
