@@ -14,7 +14,8 @@ still back-propagating (engine.PairStep), the rest follows at the end.
 
 Gradients are WRITTEN into their flat slice by the kernels that compute them (every parameter of KPFCNN is produced by
 one of this package's autograd Functions, which take the destination through `param._d3f_grad`): no zero-fill, no
-per-parameter accumulate kernel.  `verify_direct()` proves that property for a model (NaN-poison, one step, scan).
+per-parameter accumulate kernel.  `verify_direct()` proves that property for a model (it records which destinations the
+kernels of one step actually fetched).
 """
 import torch
 import torch.distributed as dist
@@ -59,7 +60,7 @@ class FlatSGD:
             g = self.flat_g[off:off + p.numel()].view_as(p)
             p.grad = g
             if direct:
-                g._d3f_prezeroed = True  # the optimiser kernel clears the flat gradient: kernels may accumulate into it
+                g._d3f_prezeroed = True  # zero_grad() clears the flat gradient once per step: kernels may accumulate into it
                 p._d3f_grad = g          # destination the backward kernels write into (ops.grad_dst)
         self.direct = direct
         self.lr = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
